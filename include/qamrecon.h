@@ -1,0 +1,181 @@
+/*
+ * qamrecon.h -- C ABI of libqamrecon.so, the B200 (sm_100a) implementation of the
+ * reverse-reconciliation hot path of moriglia/qam-reconciliation.
+ *
+ * The reference has no FFI: its boundary is the Python API of its Cython extension
+ * classes (qamreconciliation/__init__.py:1-4).  Each entry point below names the
+ * reference method it stands behind (file:line relative to the reference checkout);
+ * the Python classes in qam-reconciliation_b200/qamreconciliation/ bind these through
+ * ctypes with the reference's names and argument order.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `d_` = device pointer, `h_` = host pointer.
+ *   - every array is caller-allocated; the library never frees caller memory.
+ *   - batched arrays are row-major [frames][per-frame length].
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); work is
+ *     enqueued on it and NOT synchronised unless stated.
+ *   - return value: QR_OK or an error code; qr_last_error() gives the message of the
+ *     last failure on the calling thread.
+ *   - dtype codes: QR_F32 / QR_F64 for LLR-like arrays.
+ *   - there is no CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef QAMRECON_H
+#define QAMRECON_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QR_OK 0
+#define QR_ERR_INVALID 1  /* bad argument or size mismatch (Python: ValueError)   */
+#define QR_ERR_GRAPH 2    /* malformed Tanner graph            (Python: ValueError)   */
+#define QR_ERR_CUDA 3     /* CUDA runtime failure              (Python: RuntimeError) */
+#define QR_ERR_NOMEM 4    /* allocation failure                (Python: MemoryError)  */
+
+#define QR_F32 32
+#define QR_F64 64
+
+/* demap modes for qr_demap_lappr */
+#define QR_DEMAP_EXACT 0      /* replays the reference's 1e-9 bisection (noisemapper.pyx:310-345) */
+#define QR_DEMAP_FAST 1       /* safeguarded Newton on F_Y, then the same dyadic cell as the bisection */
+#define QR_DEMAP_CORRECTED 2  /* flag bit: divide the k<j exponent by 2*sigma^2 too (fixes noisemapper.pyx:503-507) */
+
+/* decoder schedules (qr_decoder_set_schedule) */
+#define QR_SCHED_PERSISTENT 0 /* one cooperative kernel per batch, grid barriers between phases */
+#define QR_SCHED_LAUNCH 1     /* one check + one variable kernel launch per iteration */
+
+typedef struct qr_graph qr_graph;
+typedef struct qr_decoder qr_decoder;
+typedef struct qr_mapper qr_mapper;
+
+int qr_abi_version(void);
+const char *qr_last_error(void);
+int qr_device_count(int *count);
+
+/* ---------------------------------------------------------------- Tanner graph
+ * Replaces Decoder.__cinit__ (decoder.pyx:93-146) and Matrix.__cinit__ (matrix.pyx:21-38):
+ * vid/cid are the reference's e_to_v / e_to_c edge arrays (host, int64, length n_edges).
+ * O(E) counting sort instead of the reference's O(nodes*E) scan (decoder.pyx:60-89);
+ * per-node edge lists keep the reference's ascending-edge-id order (:73-76).
+ * Unlike the reference it validates: ids >= 0, every check degree >= 2, no id gaps.
+ * device < 0 builds the host tables only (no CUDA call), for tests. */
+int qr_graph_create(const int64_t *h_vid, const int64_t *h_cid, int64_t n_edges, int device,
+                    qr_graph **out);
+void qr_graph_destroy(qr_graph *g);
+/* Decoder.cnum/vnum/ednum (decoder.pyx:157-172), Matrix.cnum/vnum/ednum (matrix.pxd:24-27) */
+int qr_graph_info(const qr_graph *g, int64_t *n_vars, int64_t *n_checks, int64_t *n_edges,
+                  int32_t *max_check_degree, int32_t *max_var_degree);
+/* host copies of the device tables (any pointer may be NULL):
+ *   chk_order[C]   internal check slot -> original check id (slots sorted by degree, then id)
+ *   slot_edge[E]   CSR slot -> original edge id (slots grouped by internal check, ascending edge id)
+ *   slot_var[E]    CSR slot -> variable id
+ *   var_ptr[N+1], var_slot[E]  per variable: CSR slots of its edges in ascending edge id */
+int qr_graph_export(const qr_graph *g, int32_t *chk_order, int32_t *slot_edge, int32_t *slot_var,
+                    int32_t *var_ptr, int32_t *var_slot);
+
+/* ---------------------------------------------------------------- syndrome
+ * Matrix.eval_syndrome (matrix.pyx:55-60), batched: synd[b][c] = XOR of word[b][v] over the
+ * check's edges (whole bytes are XOR-ed, as the reference does). */
+int qr_eval_syndrome(const qr_graph *g, const uint8_t *d_word, uint8_t *d_synd, int64_t frames,
+                     void *stream);
+/* Decoder.check_word (decoder.pyx:220-232) / check_lappr (decoder.pyx:260-281), batched:
+ * ok[b] = 1 iff every check sees synd XOR parity == 0; lappr bit = (lappr < 0) (decoder.pyx:244). */
+int qr_check_word(const qr_graph *g, const uint8_t *d_word, const uint8_t *d_synd, int64_t frames,
+                  uint8_t *d_ok, void *stream);
+int qr_check_lappr(const qr_graph *g, const void *d_lappr, int dtype, const uint8_t *d_synd,
+                   int64_t frames, uint8_t *d_ok, void *stream);
+/* utils.count_errors_from_lappr (utils.pyx:27-40), batched over the first `k` bits of each frame:
+ * errors[b] = #{i<k : (lappr[b][i] >= 0 ? 0 : 1) != word[b][i]}. */
+int qr_count_errors(const void *d_lappr, int dtype, const uint8_t *d_word, int64_t frames,
+                    int64_t frame_len, int64_t k, int32_t *d_errors, void *stream);
+
+/* ---------------------------------------------------------------- decoder
+ * Decoder._decode / decode (decoder.pyx:391-455), batched over independent frames.
+ * precision QR_F64: the reference's box-plus recursion in double, same association order;
+ * precision QR_F32: fast mode (exp-domain forward/backward products, float messages).
+ * `lanes` = frames resident at once (rounded up to a multiple of 32; 0 = library default). */
+int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decoder **out);
+void qr_decoder_destroy(qr_decoder *d);
+int qr_decoder_set_schedule(qr_decoder *d, int schedule);
+/* llr [frames][N] (QR_F32|QR_F64), synd [frames][C]; outputs success[frames] (u8), iters[frames]
+ * (i32), post [frames][N] (QR_F32|QR_F64, may be NULL).  Semantics per frame are the reference's:
+ * (1,0,input) if the input already satisfies the syndrome; (1,t) with the posteriors of iteration t
+ * on success; (0,max_iterations) with the last posteriors otherwise. */
+int qr_decode_batch(qr_decoder *d, const void *d_llr, int llr_dtype, const uint8_t *d_synd,
+                    int64_t frames, int32_t max_iterations, uint8_t *d_success, int32_t *d_iters,
+                    void *d_post, int post_dtype, void *stream);
+/* counters of the LAST qr_decode_batch on this handle (synchronises the stream):
+ * flooding iterations summed over frames, and schedule steps executed */
+int qr_decoder_last_stats(qr_decoder *d, int64_t *frame_iterations, int64_t *steps);
+
+/* Single-node entry points the reference keeps for its unit tests (decoder.pyx:190-217,
+ * 301-319, 372-388); device arrays are fp64 and updated in place like the caller's numpy
+ * arrays are in the reference.  They run the same device functions as the QR_F64 decoder. */
+int qr_process_check_node(const qr_graph *g, int64_t check, const uint8_t *d_synd, double *d_c2v,
+                          const double *d_v2c, void *stream);
+int qr_process_var_node(const qr_graph *g, int64_t var, const double *d_llr, const double *d_c2v,
+                        double *d_v2c, double *d_post, void *stream);
+int qr_check_synd_node(const qr_graph *g, int64_t check, const uint8_t *d_word,
+                       const uint8_t *d_synd, uint8_t *d_ok, void *stream);
+
+/* ---------------------------------------------------------------- noise mapper
+ * NoiseMapper.__cinit__ tables (noisemapper.pyx:103-236) for a PAM alphabet
+ * (alphabet.pyx:35-76): constellation[order], thresholds[order+1], probabilities[order],
+ * sign_config[order] (host arrays).  Tables are computed on the device with the same erf
+ * the kernels use. */
+int qr_mapper_create(int bits_per_symbol, const double *h_constellation, const double *h_thresholds,
+                     const double *h_probabilities, double noise_var, const uint8_t *h_sign_config,
+                     int device, qr_mapper **out);
+void qr_mapper_destroy(qr_mapper *m);
+/* host copies: F_Y_thresholds[order+1], delta_F_Y[order], fwrd[order*order], back[order*order],
+ * bare_llr_table[order*bps], inf_erf_table[order*order] (noisemapper.pxd:19-35); NULL to skip */
+int qr_mapper_tables(const qr_mapper *m, double *F_Y_thresholds, double *delta_F_Y, double *fwrd,
+                     double *back, double *bare_llr_table, double *inf_erf_table);
+
+/* NoiseMapper.hard_decide_index (noisemapper.pyx:349-359) */
+int qr_hard_decide_index(const qr_mapper *m, const double *d_y, int64_t n, int64_t *d_index,
+                         void *stream);
+/* PAMAlphabet.demap_symbols_to_bits (alphabet.pyx:98-107): bits[i*bps+k] */
+int qr_symbols_to_bits(const qr_mapper *m, const int64_t *d_index, int64_t n, uint8_t *d_bits,
+                       void *stream);
+/* NoiseMapper.map_noise (noisemapper.pyx:373-388) */
+int qr_map_noise(const qr_mapper *m, const double *d_y, const int64_t *d_index, int64_t n,
+                 double *d_n_hat, void *stream);
+/* the three above fused in one pass over y (any output may be NULL) */
+int qr_front_end(const qr_mapper *m, const double *d_y, int64_t n, int64_t *d_index,
+                 double *d_n_hat, uint8_t *d_bits, void *stream);
+/* NoiseMapper.demap_lappr_array (noisemapper.pyx:544-559), output scaled by alpha
+ * (sims/reconciliation.pyx:144-145); llr [n*bps] as QR_F32 or QR_F64 */
+int qr_demap_lappr(const qr_mapper *m, const double *d_n_hat, const int64_t *d_tx_index, int64_t n,
+                   int mode, double alpha, void *d_llr, int llr_dtype, void *stream);
+/* NoiseMapper.g_inv_search (noisemapper.pyx:310-345) for n values and one region index each */
+int qr_g_inv_search(const qr_mapper *m, const double *d_n_hat, const int64_t *d_region, int64_t n,
+                    int mode, double *d_y_hat, void *stream);
+/* NoiseMapper.bare_llr (noisemapper.pyx:423-432) */
+int qr_bare_llr(const qr_mapper *m, const int64_t *d_tx_index, int64_t n, void *d_llr,
+                int llr_dtype, void *stream);
+/* direct-reconciliation LLR (sims/reconciliation.pyx:25-72); two_variance = Es*10^(-snr/10) */
+int qr_direct_llr(const qr_mapper *m, const double *d_y, int64_t n, double two_variance,
+                  void *d_llr, int llr_dtype, void *stream);
+
+/* ---------------------------------------------------------------- whole path, host buffers
+ * One reverse-reconciliation pass over `frames` frames held in HOST memory (pinned memory makes
+ * the copies asynchronous), the chain of sims/reconciliation.pyx:129-153:
+ *   y -> hard decision -> softening metric, bits -> syndrome -> Alice's LLR (from her symbols
+ *   h_tx_index) * alpha -> syndrome decoding.
+ * reconciliation mode: 0 soft reverse, 1 hard reverse (bare_llr), 2 soft direct.
+ * Outputs (host, any may be NULL): success[frames], iters[frames], post[frames][N] (post_dtype),
+ * word[frames][N] (the bits the syndrome was taken of), bit_errors[frames] over the first k_info bits.
+ * Copies, kernels and the final synchronisation all happen inside the call. */
+int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha,
+                      const double *h_y, const int64_t *h_tx_index, int64_t frames,
+                      int32_t max_iterations, int64_t k_info, uint8_t *h_success, int32_t *h_iters,
+                      void *h_post, int post_dtype, uint8_t *h_word, int32_t *h_bit_errors,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QAMRECON_H */

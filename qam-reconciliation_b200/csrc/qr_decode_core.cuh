@@ -1,0 +1,520 @@
+// Per-work-item device functions of the syndrome sum-product decoder
+// (reference: qamreconciliation/decoder.pyx:285-298, 322-369, 235-257, 391-436).
+//
+// DATA LAYOUT (one decoder workspace, `lanes` = L frames resident, L % 32 == 0):
+//   c2v  [E][L]  check-to-variable messages, row = CSR slot (edges grouped by check, checks
+//                sorted by degree; within a check ascending original edge id), frames innermost
+//   post [N][L]  a-posteriori LLRs             llr [N][L]  channel LLRs
+//   synd [C][L]  syndrome bytes, row = internal check slot
+// A work item is (node, lane-vector): one thread owns VEC consecutive lanes of one node and moves
+// them with one 128-bit access per row, so a warp reads/writes whole 128 B lines of a row.
+//
+// Only ONE message array is stored.  The reference's variable update writes
+// v2c[e] = post[v] - c2v[e] (decoder.pyx:295-297); the check phase recomputes exactly that
+// expression from post and the previous c2v, so the v2c array never exists in memory and the
+// fp64 results are bit-identical to the two-array schedule.
+//
+// A lane runs one frame at a time.  State per lane (double-buffered by step parity, because the
+// variable phase reads the old state while one thread per lane writes the new one):
+//   frame  frame id (-1: idle)      iter  completed variable updates      fresh  1 until the lane's
+//   columns of llr/post/synd have been loaded (while fresh: c2v == 0, post == llr == input row).
+// One schedule step = check phase then variable phase:
+//   check phase, lane at iteration t: tests the syndrome on post_t (decoder.pyx:235-257) and
+//       computes c2v_{t+1} from v2c_t = post_t - c2v_t (decoder.pyx:322-369).
+//   variable phase: if the syndrome test passed -> frame done, (success=1, iters=t, post_t)
+//       (decoder.pyx:402-405 for t=0, :431-433 for t>0); else if t == max_iterations -> done,
+//       (0, max_iterations, post_t) (:435-436); else post_{t+1} = llr + sum c2v_{t+1}
+//       (decoder.pyx:291-293).  A finished lane writes its posteriors out and takes the next
+//       frame of the batch (continuous batching; no message columns are ever moved).
+//
+// Everything here is __host__ __device__ so tests/emu can run the same code on the CPU.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include "qr_common.h"
+
+namespace qr {
+
+struct LaneState {
+    int32_t frame;
+    int32_t iter;
+    int32_t fresh;
+    int32_t pad;
+};
+
+enum : int { CTRL_NEXT_FRAME = 0, CTRL_REMAINING = 1, CTRL_WORDS = 8 };
+
+template <typename T>
+struct DecodeParams {
+    // graph (device pointers)
+    const CheckBin *bins;
+    int32_t n_bins;
+    const int32_t *chk_order, *slot_var, *var_ptr, *var_slot;
+    int64_t N, C, E;
+    // workspace
+    int32_t lanes;
+    T *c2v, *post, *llr;
+    uint8_t *synd;
+    LaneState *st[2];
+    int32_t *unsat[2];
+    // batch
+    const void *llr_in;
+    int32_t llr_in_f64;
+    const uint8_t *synd_in;
+    int64_t frames;
+    int32_t maxiter;
+    uint8_t *success;
+    int32_t *iters;
+    void *post_out;
+    int32_t post_out_f64;
+    // control words and counters
+    int32_t *ctrl;
+    unsigned long long *stats;  // [0] flooding iterations summed over finished frames
+};
+
+// ---------------------------------------------------------------------------------------------
+// vectors of VEC lanes
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) Vec {
+    T v[VEC];
+};
+
+// L2-only (.cg) accesses for data other SMs wrote in the previous phase (messages, posteriors):
+// each value is read once per phase, so keeping it out of L1 leaves L1 to the index tables.
+template <typename V>
+QR_HD V ld_stream(const V *p)
+{
+#if defined(__CUDA_ARCH__)
+    static_assert(sizeof(V) == 4 || sizeof(V) == 8 || sizeof(V) == 16, "vector width");
+    V r;
+    if constexpr (sizeof(V) == 16) {
+        int4 t = __ldcg(reinterpret_cast<const int4 *>(p));
+        memcpy(&r, &t, 16);
+    } else if constexpr (sizeof(V) == 8) {
+        int2 t = __ldcg(reinterpret_cast<const int2 *>(p));
+        memcpy(&r, &t, 8);
+    } else {
+        int t = __ldcg(reinterpret_cast<const int *>(p));
+        memcpy(&r, &t, 4);
+    }
+    return r;
+#else
+    return *p;
+#endif
+}
+template <typename V>
+QR_HD void st_stream(V *p, const V &val)
+{
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(V) == 16) {
+        int4 t; memcpy(&t, &val, 16);
+        __stcg(reinterpret_cast<int4 *>(p), t);
+    } else if constexpr (sizeof(V) == 8) {
+        int2 t; memcpy(&t, &val, 8);
+        __stcg(reinterpret_cast<int2 *>(p), t);
+    } else {
+        int t; memcpy(&t, &val, 4);
+        __stcg(reinterpret_cast<int *>(p), t);
+    }
+#else
+    *p = val;
+#endif
+}
+
+template <typename T, int VEC>
+QR_HD Vec<T, VEC> ld_row(const T *base, int64_t row, int32_t lanes, int32_t l0)
+{
+    return ld_stream(reinterpret_cast<const Vec<T, VEC> *>(base + row * lanes + l0));
+}
+template <typename T, int VEC>
+QR_HD void st_row(T *base, int64_t row, int32_t lanes, int32_t l0, const Vec<T, VEC> &v)
+{
+    st_stream(reinterpret_cast<Vec<T, VEC> *>(base + row * lanes + l0), v);
+}
+
+template <typename T>
+QR_HD T load_input_llr(const void *llr_in, int is_f64, int64_t idx);
+
+template <>
+QR_HD double load_input_llr<double>(const void *llr_in, int is_f64, int64_t idx)
+{
+    return is_f64 ? static_cast<const double *>(llr_in)[idx]
+                  : (double)static_cast<const float *>(llr_in)[idx];
+}
+
+// fp32 mode saturates what it reads: +-inf or 1e300 (the reference's bare_llr_table sentinel,
+// noisemapper.pyx:217-218) would otherwise turn into inf - inf = NaN in the sums.
+constexpr float kLlrInClamp = 1.0e30f;
+constexpr float kMsgClamp = 80.0f;  // |c2v| cap: exp(-80) is still a normal float
+
+template <>
+QR_HD float load_input_llr<float>(const void *llr_in, int is_f64, int64_t idx)
+{
+    float x = is_f64 ? (float)static_cast<const double *>(llr_in)[idx]
+                     : static_cast<const float *>(llr_in)[idx];
+    return fminf(fmaxf(x, -kLlrInClamp), kLlrInClamp);
+}
+
+QR_HD void store_output_llr(void *out, int is_f64, int64_t idx, double v)
+{
+    if (is_f64) static_cast<double *>(out)[idx] = v;
+    else static_cast<float *>(out)[idx] = (float)v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// check-node arithmetic
+//
+// MathRef: the reference's box-plus, evaluated exactly as written at decoder.pyx:41-45,
+//   sgn(a)sgn(b)min(|a|,|b|) + log(1+exp(-|a+b|)) - log(1+exp(-|a-b|))   (left to right),
+// in the forward/backward recursion of decoder.pyx:341-367.
+struct MathRef {
+    using T = double;
+    static QR_HD int sgn(double x) { return (0.0 < x) - (x < 0.0); }
+    static QR_HD double box_plus(double a, double b)
+    {
+        double fa = fabs(a), fb = fabs(b);
+        double mn = (fb < fa) ? fb : fa;
+        double r = (double)(sgn(a) * sgn(b)) * mn;
+        r = r + log(1 + exp(-fabs(a + b)));
+        r = r - log(1 + exp(-fabs(a - b)));
+        return r;
+    }
+    // x[0..deg) holds v2c on entry, c2v on exit; bwd is scratch of >= deg entries
+    template <int UNR>
+    static QR_HD void check_node(int deg, double *x, double *bwd, bool synd)
+    {
+        bwd[deg - 1] = x[deg - 1];
+#pragma unroll UNR
+        for (int i = deg - 2; i >= 1; --i) bwd[i] = box_plus(bwd[i + 1], x[i]);
+        const double pre = synd ? -1.0 : 1.0;
+        double fwd = x[0];
+        x[0] = pre * bwd[1];
+#pragma unroll UNR
+        for (int i = 1; i < deg - 1; ++i) {
+            double out = pre * box_plus(fwd, bwd[i + 1]);
+            fwd = box_plus(fwd, x[i]);
+            x[i] = out;
+        }
+        x[deg - 1] = pre * fwd;
+    }
+};
+
+// MathFast: float.  A message of magnitude m is carried as u = exp(-m) in [0,1]; the box-plus of
+// magnitudes is then u_a (+) u_b = (u_a + u_b) / (1 + u_a u_b)  [tanh(m/2) = (1-u)/(1+u)], which has
+// no cancellation at large m.  Partial results stay as fractions n/d so the recursion is FMAs only;
+// one ex2 per incoming and two lg2 per outgoing message are the only special-function ops.
+// Signs: product of the other edges' sign bits, times the syndrome bit (decoder.pyx:358-367).
+struct MathFast {
+    using T = float;
+    static QR_HD float ex2(float x)
+    {
+#if defined(__CUDA_ARCH__)
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+#else
+        return exp2f(x);
+#endif
+    }
+    static QR_HD float lg2(float x)
+    {
+#if defined(__CUDA_ARCH__)
+        float r;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+#else
+        return log2f(x);
+#endif
+    }
+    static QR_HD uint32_t bits(float x)
+    {
+        uint32_t b;
+        memcpy(&b, &x, 4);
+        return b;
+    }
+    static QR_HD float emit(float n, float d, uint32_t sign_bit)
+    {
+        float mag = 0.69314718056f * (lg2(d) - lg2(n));
+        mag = fminf(fmaxf(mag, 0.0f), kMsgClamp);  // also maps NaN/inf to the clamp
+        uint32_t b = bits(mag) | sign_bit;
+        float r;
+        memcpy(&r, &b, 4);
+        return r;
+    }
+    // x[0..deg): v2c in, c2v out.  u/nb/db: scratch of >= deg entries each.
+    template <int UNR>
+    static QR_HD void check_node(int deg, float *x, float *u, float *nb, float *db, bool synd)
+    {
+        uint32_t total = synd ? 0x80000000u : 0u;
+#pragma unroll UNR
+        for (int i = 0; i < deg; ++i) {
+            total ^= bits(x[i]) & 0x80000000u;
+            u[i] = ex2(-1.44269504089f * fabsf(x[i]));
+        }
+        // backward fractions B_i = u_i (+) ... (+) u_{deg-1} = nb[i] / db[i]
+        nb[deg - 1] = u[deg - 1];
+        db[deg - 1] = 1.0f;
+#pragma unroll UNR
+        for (int i = deg - 2; i >= 1; --i) {
+            nb[i] = fmaf(u[i], db[i + 1], nb[i + 1]);
+            db[i] = fmaf(u[i], nb[i + 1], db[i + 1]);
+            if (UNR == 1 && db[i] > 1.0e18f) {  // run-time high degrees only: renormalise
+                nb[i] *= 1.0e-18f;
+                db[i] *= 1.0e-18f;
+            }
+        }
+        float nf = u[0], df = 1.0f;  // forward fraction F_{i-1}
+        x[0] = emit(nb[1], db[1], total ^ (bits(x[0]) & 0x80000000u));
+#pragma unroll UNR
+        for (int i = 1; i < deg - 1; ++i) {
+            const float n = fmaf(nf, db[i + 1], nb[i + 1] * df);
+            const float d = fmaf(nf, nb[i + 1], df * db[i + 1]);
+            x[i] = emit(n, d, total ^ (bits(x[i]) & 0x80000000u));
+            const float nf2 = fmaf(u[i], df, nf);
+            df = fmaf(u[i], nf, df);
+            nf = nf2;
+            if (UNR == 1 && df > 1.0e18f) {
+                nf *= 1.0e-18f;
+                df *= 1.0e-18f;
+            }
+        }
+        x[deg - 1] = emit(nf, df, total ^ (bits(x[deg - 1]) & 0x80000000u));
+    }
+};
+
+template <typename T>
+struct MathOf;
+template <>
+struct MathOf<double> {
+    using M = MathRef;
+    template <int CAP, int UNR>
+    static QR_HD void run(int deg, double *x, bool synd)
+    {
+        double bwd[CAP];
+        MathRef::check_node<UNR>(deg, x, bwd, synd);
+    }
+};
+template <>
+struct MathOf<float> {
+    using M = MathFast;
+    template <int CAP, int UNR>
+    static QR_HD void run(int deg, float *x, bool synd)
+    {
+        float u[CAP], nb[CAP], db[CAP];
+        MathFast::check_node<UNR>(deg, x, u, nb, db, synd);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-thread view of its VEC lanes, loaded once per phase
+template <int VEC>
+struct LaneInfo {
+    int32_t l0;
+    int32_t frame[VEC];
+    int32_t iter[VEC];
+    uint32_t active;  // bit k: lane runs a frame
+    uint32_t fresh;   // bit k: lane's columns are not loaded yet
+    // variable phase decisions
+    uint32_t fin_ok, fin_fail, upd;
+};
+
+template <typename T, int VEC>
+QR_HD LaneInfo<VEC> load_lane_info(const DecodeParams<T> &P, int cur, int32_t jv)
+{
+    LaneInfo<VEC> L;
+    L.l0 = jv * VEC;
+    L.active = L.fresh = L.fin_ok = L.fin_fail = L.upd = 0;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        const LaneState s = ld_stream(&P.st[cur][L.l0 + k]);
+        L.frame[k] = s.frame;
+        L.iter[k] = s.iter;
+        if (s.frame >= 0) {
+            L.active |= 1u << k;
+            if (s.fresh) L.fresh |= 1u << k;
+        }
+    }
+    return L;
+}
+
+template <typename T, int VEC>
+QR_HD void decide_lanes(const DecodeParams<T> &P, int cur, LaneInfo<VEC> &L)
+{
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        if (!(L.active >> k & 1)) continue;
+        if (ld_stream(&P.unsat[cur][L.l0 + k]) == 0) L.fin_ok |= 1u << k;
+        else if (L.iter[k] >= P.maxiter) L.fin_fail |= 1u << k;
+        else L.upd |= 1u << k;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CHECK PHASE item: internal check `ci` (degree deg, first CSR slot slot0) for the thread's lanes.
+// Returns a bit per lane: 1 = this check is NOT satisfied by the lane's current posteriors.
+// D > 0: compile-time degree (registers); D == 0: run-time degree <= kMaxCheckDegree.
+template <typename T, int VEC, int D>
+QR_HD uint32_t check_item(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t ci, int32_t slot0,
+                          int32_t deg_rt)
+{
+    constexpr int CAP = D > 0 ? D : kMaxCheckDegree;
+    constexpr int UNR = D > 0 ? D : 1;  // full unroll for compile-time degrees, none otherwise
+    const int deg = D > 0 ? D : deg_rt;
+    const int32_t lanes = P.lanes;
+    Vec<T, VEC> x[CAP];  // per edge: v2c in, c2v out
+    uint32_t par = 0;    // bit k: parity of negative posteriors XOR syndrome
+    uint8_t sy[VEC];
+    {
+        const uint8_t *row = P.synd + (int64_t)ci * lanes + L.l0;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) sy[k] = row[k];
+    }
+    if (L.fresh) {
+        const int32_t c_orig = P.chk_order[ci];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+            if (L.fresh >> k & 1) {
+                sy[k] = P.synd_in[(int64_t)L.frame[k] * P.C + c_orig];
+                P.synd[(int64_t)ci * lanes + L.l0 + k] = sy[k];
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) par |= (uint32_t)(sy[k] & 1u) << k;
+
+#pragma unroll UNR
+    for (int i = 0; i < deg; ++i) {
+        const int32_t v = P.slot_var[slot0 + i];
+        Vec<T, VEC> pv = ld_row<T, VEC>(P.post, v, lanes, L.l0);
+        Vec<T, VEC> cv = ld_row<T, VEC>(P.c2v, slot0 + i, lanes, L.l0);
+        if (L.fresh) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                if (L.fresh >> k & 1) {
+                    pv.v[k] = load_input_llr<T>(P.llr_in, P.llr_in_f64, (int64_t)L.frame[k] * P.N + v);
+                    cv.v[k] = (T)0;
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            par ^= (uint32_t)(pv.v[k] < (T)0) << k;      // decoder.pyx:244 (strict <)
+            x[i].v[k] = pv.v[k] - cv.v[k];               // decoder.pyx:295-297
+        }
+    }
+    // node update, one lane at a time (keeps only one lane's scratch live)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        T xs[CAP];
+#pragma unroll UNR
+        for (int i = 0; i < deg; ++i) xs[i] = x[i].v[k];
+        MathOf<T>::template run<CAP, UNR>(deg, xs, (sy[k] & 1u) != 0);
+#pragma unroll UNR
+        for (int i = 0; i < deg; ++i) x[i].v[k] = xs[i];
+    }
+#pragma unroll UNR
+    for (int i = 0; i < deg; ++i) st_row<T, VEC>(P.c2v, slot0 + i, lanes, L.l0, x[i]);
+    return par & L.active;
+}
+
+// syndrome byte semantics: the reference XORs the whole byte and tests (parity ^ 1) != 0
+// (decoder.pyx:243-249); for the 0/1 bytes every caller passes that is the low bit, which is
+// what the kernels use.
+
+// ---------------------------------------------------------------------------------------------
+// VARIABLE PHASE item: variable n for the thread's lanes (decisions already in L).
+template <typename T, int VEC>
+QR_HD void var_item(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t n)
+{
+    const int32_t lanes = P.lanes;
+    const uint32_t fin = L.fin_ok | L.fin_fail;
+    if (fin) {
+        // finished lanes: the posteriors of the iteration that ended the frame go to the caller
+        Vec<T, VEC> old_post;
+        if (fin & ~L.fresh) old_post = ld_row<T, VEC>(P.post, n, lanes, L.l0);
+        if (P.post_out) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                if (fin >> k & 1) {
+                    const int64_t idx = (int64_t)L.frame[k] * P.N + n;
+                    if (L.fresh >> k & 1) {
+                        // A frame that never iterated.  Input already consistent: the reference copies
+                        // it (decoder.pyx:404), bit for bit when both sides are fp64.  max_iterations
+                        // == 0: the reference still ran its first variable pass with c2v == 0
+                        // (decoder.pyx:420-421), i.e. llr + 0.0 per edge, which turns -0.0 into +0.0.
+                        const bool copied = (L.fin_ok >> k & 1) != 0;
+                        if (copied && P.llr_in_f64 && P.post_out_f64) {
+                            static_cast<double *>(P.post_out)[idx] = static_cast<const double *>(P.llr_in)[idx];
+                        } else {
+                            double val = (double)load_input_llr<T>(P.llr_in, P.llr_in_f64, idx);
+                            if (!copied && P.var_ptr[n + 1] > P.var_ptr[n]) val = val + 0.0;
+                            store_output_llr(P.post_out, P.post_out_f64, idx, val);
+                        }
+                    } else {
+                        store_output_llr(P.post_out, P.post_out_f64, idx, (double)old_post.v[k]);
+                    }
+                }
+        }
+    }
+    if (L.upd) {
+        Vec<T, VEC> acc = ld_row<T, VEC>(P.llr, n, lanes, L.l0);
+        if (L.fresh & L.upd) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                if ((L.fresh & L.upd) >> k & 1)
+                    acc.v[k] = load_input_llr<T>(P.llr_in, P.llr_in_f64, (int64_t)L.frame[k] * P.N + n);
+            st_row<T, VEC>(P.llr, n, lanes, L.l0, acc);  // the other lanes rewrite their own value
+        }
+        const int32_t q0 = P.var_ptr[n], q1 = P.var_ptr[n + 1];
+        for (int32_t q = q0; q < q1; ++q) {               // ascending edge id: decoder.pyx:291-293
+            Vec<T, VEC> m = ld_row<T, VEC>(P.c2v, P.var_slot[q], lanes, L.l0);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc.v[k] = acc.v[k] + m.v[k];
+        }
+        // lanes that did not update (idle or just finished) receive junk: nothing reads their
+        // posterior column again before a new frame overwrites it
+        st_row<T, VEC>(P.post, n, lanes, L.l0, acc);
+    }
+}
+
+// One thread per lane-vector (the one that owns variable 0) advances the lane state machine.
+#if defined(__CUDA_ARCH__)
+#define QR_ATOMIC_ADD_I32(p, v) atomicAdd((p), (v))
+#define QR_ATOMIC_ADD_U64(p, v) atomicAdd((p), (v))
+#else
+#define QR_ATOMIC_ADD_I32(p, v) ([&] { int32_t _o = *(p); *(p) += (v); return _o; }())
+#define QR_ATOMIC_ADD_U64(p, v) ([&] { unsigned long long _o = *(p); *(p) += (v); return _o; }())
+#endif
+
+template <typename T, int VEC>
+QR_HD void bookkeep_lanes(const DecodeParams<T> &P, int cur, const LaneInfo<VEC> &L)
+{
+    const int nxt = cur ^ 1;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        const int32_t lane = L.l0 + k;
+        LaneState s;
+        s.frame = L.frame[k];
+        s.iter = L.iter[k];
+        s.fresh = (L.fresh >> k) & 1;
+        s.pad = 0;
+        if ((L.fin_ok | L.fin_fail) >> k & 1) {
+            const bool ok = (L.fin_ok >> k & 1) != 0;
+            P.success[s.frame] = ok ? 1 : 0;
+            P.iters[s.frame] = ok ? s.iter : P.maxiter;
+            QR_ATOMIC_ADD_U64(&P.stats[0], (unsigned long long)s.iter);
+            QR_ATOMIC_ADD_I32(&P.ctrl[CTRL_REMAINING], -1);
+            int32_t nf = QR_ATOMIC_ADD_I32(&P.ctrl[CTRL_NEXT_FRAME], 1);
+            if ((int64_t)nf < P.frames) { s.frame = nf; s.iter = 0; s.fresh = 1; }
+            else { s.frame = -1; s.iter = 0; s.fresh = 0; }
+        } else if (L.upd >> k & 1) {
+            s.iter += 1;
+            s.fresh = 0;
+        }
+        P.st[nxt][lane] = s;
+        P.unsat[nxt][lane] = 0;
+    }
+}
+
+}  // namespace qr

@@ -1,0 +1,96 @@
+// Host-side construction of the graph tables (pure C++, no CUDA): shared by libqamrecon
+// (qr_graph.cu) and by the CPU emulation harness under tests/emu.
+#pragma once
+
+#include <algorithm>
+
+#include "qr_common.h"
+
+namespace qr {
+
+inline int build_host_tables(qr_graph &g, const int64_t *vid, const int64_t *cid, int64_t E)
+{
+    if (!vid || !cid) return fail(QR_ERR_INVALID, "null edge array");
+    if (E <= 0) return fail(QR_ERR_GRAPH, "edge list is empty");
+    if (E >= (int64_t(1) << 31)) return fail(QR_ERR_GRAPH, "more than 2^31-1 edges");
+    int64_t C = 0, N = 0;
+    for (int64_t e = 0; e < E; ++e) {
+        if (vid[e] < 0 || cid[e] < 0) return fail(QR_ERR_GRAPH, "negative node id in edge list");
+        C = std::max(C, cid[e] + 1);
+        N = std::max(N, vid[e] + 1);
+    }
+    if (C >= (int64_t(1) << 31) || N >= (int64_t(1) << 31))
+        return fail(QR_ERR_GRAPH, "node id does not fit 31 bits");
+    g.N = N; g.C = C; g.E = E;
+
+    std::vector<int32_t> cdeg(C, 0), vdeg(N, 0);
+    for (int64_t e = 0; e < E; ++e) { cdeg[cid[e]]++; vdeg[vid[e]]++; }
+    g.max_cdeg = *std::max_element(cdeg.begin(), cdeg.end());
+    g.max_vdeg = *std::max_element(vdeg.begin(), vdeg.end());
+    for (int64_t c = 0; c < C; ++c) {
+        // the reference indexes its 2*(deg-1) scratch out of bounds for degree 1 and dereferences a
+        // failed malloc for degree 0 (decoder.pyx:131-135, :337-342): reject instead
+        if (cdeg[c] < 2) {
+            char b[160];
+            snprintf(b, sizeof(b), "check node %lld has degree %d; every check needs degree >= 2",
+                     (long long)c, cdeg[c]);
+            return fail(QR_ERR_GRAPH, b);
+        }
+    }
+    if (g.max_cdeg > kMaxCheckDegree) {
+        char b[160];
+        snprintf(b, sizeof(b), "check degree %d exceeds the supported maximum %d", g.max_cdeg,
+                 kMaxCheckDegree);
+        return fail(QR_ERR_GRAPH, b);
+    }
+
+    // internal check order: by degree, ties by id (counting sort) -> one contiguous bin per degree
+    std::vector<int32_t> deg_count(g.max_cdeg + 2, 0);
+    for (int64_t c = 0; c < C; ++c) deg_count[cdeg[c] + 1]++;
+    for (int d = 0; d <= g.max_cdeg; ++d) deg_count[d + 1] += deg_count[d];
+    g.chk_order.assign(C, 0);
+    std::vector<int32_t> chk_slot(C);  // original check id -> internal slot
+    {
+        std::vector<int32_t> fill(deg_count.begin(), deg_count.end() - 1);
+        for (int64_t c = 0; c < C; ++c) {
+            int32_t s = fill[cdeg[c]]++;
+            g.chk_order[s] = (int32_t)c;
+            chk_slot[c] = s;
+        }
+    }
+    g.chk_ptr.assign(C + 1, 0);
+    for (int64_t s = 0; s < C; ++s) g.chk_ptr[s + 1] = g.chk_ptr[s] + cdeg[g.chk_order[s]];
+    g.bins.clear();
+    for (int d = 2; d <= g.max_cdeg; ++d) {
+        int32_t cnt = deg_count[d + 1] - deg_count[d];
+        if (cnt > 0) g.bins.push_back(CheckBin{d, deg_count[d], cnt, g.chk_ptr[deg_count[d]]});
+    }
+
+    g.slot_edge.assign(E, 0);
+    g.slot_var.assign(E, 0);
+    std::vector<int32_t> edge_slot(E);
+    {
+        std::vector<int32_t> fill(C, 0);
+        for (int64_t e = 0; e < E; ++e) {
+            int32_t s = chk_slot[cid[e]];
+            int32_t slot = g.chk_ptr[s] + fill[s]++;
+            g.slot_edge[slot] = (int32_t)e;
+            g.slot_var[slot] = (int32_t)vid[e];
+            edge_slot[e] = slot;
+        }
+    }
+    g.var_ptr.assign(N + 1, 0);
+    for (int64_t v = 0; v < N; ++v) g.var_ptr[v + 1] = g.var_ptr[v] + vdeg[v];
+    g.var_slot.assign(E, 0);
+    {
+        std::vector<int32_t> fill(N, 0);
+        for (int64_t e = 0; e < E; ++e) {
+            int64_t v = vid[e];
+            g.var_slot[g.var_ptr[v] + fill[v]++] = edge_slot[e];
+        }
+    }
+    return QR_OK;
+}
+
+
+}  // namespace qr

@@ -1,0 +1,51 @@
+// Opaque handle layouts shared by the translation units of libqamrecon.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "qr_common.h"
+
+namespace qr {
+struct LaneState;
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+}  // namespace qr
+
+struct qr_decoder {
+    const qr_graph *g = nullptr;
+    int precision = QR_F32;
+    int schedule = QR_SCHED_PERSISTENT;
+    int32_t lanes = 0;
+    int device = 0;
+    int regular_degree = 0;  // > 0: check-regular graph with a specialised kernel
+    void *c2v = nullptr, *post = nullptr, *llr = nullptr;
+    uint8_t *synd = nullptr;
+    qr::LaneState *st = nullptr;          // [2][lanes]
+    int32_t *unsat = nullptr;             // [2][lanes]
+    int32_t *ctrl = nullptr;              // [CTRL_WORDS]
+    unsigned long long *stats = nullptr;  // [2]
+    int32_t *h_ctrl = nullptr;            // pinned mirrors
+    unsigned long long *h_stats = nullptr;
+    cudaStream_t last_stream = nullptr;
+    int coop_grid = 0;
+    int sm_count = 0;
+    // scratch of qr_reconcile_host (grow-only)
+    void *pipe_buf = nullptr;
+    size_t pipe_cap = 0;
+};
+
+struct qr_mapper {
+    int device = 0;
+    int order = 0, bps = 0;
+    double noise_var = 0, sigma = 0, s2 = 0;
+    double *d_tables = nullptr;  // one allocation holding every table below
+    uint8_t *d_sign = nullptr;
+    double *constellation = nullptr, *thresholds = nullptr, *probabilities = nullptr;
+    double *FY_thr = nullptr, *delta = nullptr, *fwrd = nullptr, *back = nullptr, *bare = nullptr,
+           *inf_erf = nullptr;
+    size_t n_table_doubles = 0;
+};

@@ -1,0 +1,401 @@
+// Noise-mapper kernels: one thread per symbol, fp64, alphabet tables staged in shared memory.
+// (reference: qamreconciliation/noisemapper.pyx; see qr_mapper_core.cuh for the arithmetic.)
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <new>
+
+#include "qr_handles.h"
+#include "qr_mapper_core.cuh"
+
+namespace qr {
+
+static MapperView view_of(const qr_mapper *m)
+{
+    MapperView v;
+    v.order = m->order; v.bps = m->bps;
+    v.noise_var = m->noise_var; v.sigma = m->sigma; v.s2 = m->s2;
+    v.constellation = m->constellation; v.thresholds = m->thresholds; v.probabilities = m->probabilities;
+    v.sign_config = m->d_sign; v.FY_thr = m->FY_thr; v.delta = m->delta; v.bare = m->bare;
+    return v;
+}
+
+// NoiseMapper.__cinit__ tables (noisemapper.pyx:149-235), one thread: tiny and done once
+__global__ void k_mapper_tables(MapperView m, double *FY_thr, double *delta, double *fwrd, double *back,
+                                double *bare, double *inf_erf)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const int M = m.order, bps = m.bps;
+    const double *a = m.constellation, *thr = m.thresholds, *p = m.probabilities;
+    FY_thr[0] = 0;
+    FY_thr[M] = 1;
+    for (int i = 1; i < M; ++i) FY_thr[i] = mixture_cdf(a, p, M, m.s2, thr[i]);
+    for (int i = 0; i < M; ++i) delta[i] = add_rn(FY_thr[i + 1], -FY_thr[i]);
+    for (int j = 0; j < M; ++j) {
+        fwrd[j * M + 0] = 0.5 * (erf((thr[1] - a[j]) / m.s2) + 1);
+        fwrd[j * M + M - 1] = 0.5 * (1 - erf((thr[M - 1] - a[j]) / m.s2));
+        for (int i = 1; i < M - 1; ++i)
+            fwrd[j * M + i] = 0.5 * add_rn(erf((thr[i + 1] - a[j]) / m.s2), -erf((thr[i] - a[j]) / m.s2));
+    }
+    for (int i = 0; i < M; ++i)
+        for (int j = 0; j < M; ++j) {
+            double tot = 0;
+            for (int k = 0; k < M; ++k) tot = add_rn(tot, mul_rn(p[k], fwrd[k * M + i]));
+            back[i * M + j] = mul_rn(p[j], fwrd[j * M + i]) / tot;
+        }
+    for (int j = 0; j < M; ++j)
+        for (int k = 0; k < bps; ++k) {
+            double num = 0, den = 0;
+            for (int i = 0; i < M; ++i) {
+                if (gray_bit(i, k)) den = add_rn(den, fwrd[j * M + i]);
+                else num = add_rn(num, fwrd[j * M + i]);
+            }
+            bare[j * bps + k] = (den == 0) ? 1e300 : log(num / den);
+        }
+    for (int j = 0; j < M; ++j) {
+        inf_erf[0 * M + j] = -1;
+        for (int i = 1; i < M; ++i) inf_erf[i * M + j] = erf((thr[i] - a[j]) / m.s2);
+    }
+}
+
+struct SharedTables {
+    double a[kMaxOrder], p[kMaxOrder], thr[kMaxOrder + 1], FYt[kMaxOrder + 1], delta[kMaxOrder];
+    uint8_t sign[kMaxOrder];
+};
+
+__device__ __forceinline__ void stage_tables(const MapperView &m, SharedTables &s)
+{
+    for (int i = threadIdx.x; i < m.order; i += blockDim.x) {
+        s.a[i] = m.constellation[i];
+        s.p[i] = m.probabilities[i];
+        s.delta[i] = m.delta[i];
+        s.sign[i] = m.sign_config[i];
+    }
+    for (int i = threadIdx.x; i <= m.order; i += blockDim.x) {
+        s.thr[i] = m.thresholds[i];
+        s.FYt[i] = m.FY_thr[i];
+    }
+    __syncthreads();
+}
+
+// hard decision (+ softening metric) (+ Gray bits) in one pass over y
+// (noisemapper.pyx:349-359, :373-388; alphabet.pyx:98-107).  idx_in != NULL: use the given indices
+// instead of deciding (map_noise / demap_symbols_to_bits on caller-provided indices).
+__global__ void __launch_bounds__(256) k_front_end(MapperView m, const double *__restrict__ y,
+                                                   const long long *__restrict__ idx_in, int64_t n,
+                                                   long long *__restrict__ idx_out,
+                                                   double *__restrict__ n_hat, uint8_t *__restrict__ bits)
+{
+    __shared__ SharedTables s;
+    stage_tables(m, s);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        int32_t i;
+        if (idx_in) i = (int32_t)idx_in[j];
+        else i = hard_decide(s.thr, m.order, y[j]);
+        if (idx_out) idx_out[j] = i;
+        if (n_hat) {
+            const double F = mixture_cdf(s.a, s.p, m.order, m.s2, y[j]);
+            n_hat[j] = s.sign[i] ? add_rn(s.FYt[i + 1], -F) / s.delta[i] : add_rn(F, -s.FYt[i]) / s.delta[i];
+        }
+        if (bits) {
+            for (int k = 0; k < m.bps; ++k) bits[j * m.bps + k] = gray_bit(i, k);
+        }
+    }
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(128) k_demap(MapperView m, const double *__restrict__ n_hat,
+                                               const long long *__restrict__ tx, int64_t n, int mode,
+                                               double alpha, OUT *__restrict__ llr)
+{
+    __shared__ SharedTables s;
+    stage_tables(m, s);
+    const bool fast = (mode & 1) != 0, corrected = (mode & QR_DEMAP_CORRECTED) != 0;
+    const double two_s2 = 2 * m.noise_var;
+    for (int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sidx < n;
+         sidx += (int64_t)gridDim.x * blockDim.x) {
+        const double nv = n_hat[sidx];
+        const int32_t j = (int32_t)tx[sidx];
+        double N[kMaxBps], D[kMaxBps];
+        for (int k = 0; k < m.bps; ++k) { N[k] = 0; D[k] = 0; }
+        double cum = 0;
+        for (int i = 0; i < m.order; ++i) {
+            const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
+            const double yh = fast ? g_inv_fast(s.a, s.p, m.order, m.sigma, m.s2, target, 1e-9, i, cum)
+                                   : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
+            cum += s.p[i];
+            // the body of demap_from_yhat for one i (kept inline: y_hat need not be stored)
+            double sum = 0;
+            for (int k = 0; k < j; ++k) {
+                double ex = mul_rn(add_rn(add_rn(mul_rn(2, yh), -s.a[k]), -s.a[j]), add_rn(s.a[k], -s.a[j]));
+                if (corrected) ex = ex / two_s2;
+                sum = add_rn(sum, mul_rn(exp(ex), s.p[k]));
+            }
+            sum = add_rn(sum, s.p[j]);
+            for (int k = j + 1; k < m.order; ++k) {
+                const double ex =
+                    mul_rn(add_rn(add_rn(mul_rn(2, yh), -s.a[k]), -s.a[j]), add_rn(s.a[k], -s.a[j])) / two_s2;
+                sum = add_rn(sum, mul_rn(exp(ex), s.p[k]));
+            }
+            const double w = s.delta[i] / sum;
+            int q = i;
+            for (int k = 0; k < m.bps; ++k) {
+                if ((q * (q + 1)) & 3) D[k] = add_rn(D[k], w);
+                else N[k] = add_rn(N[k], w);
+                q >>= 1;
+            }
+        }
+        for (int k = 0; k < m.bps; ++k) {
+            double v = log(N[k]) - log(D[k]);
+            if (alpha != 1.0) v = mul_rn(v, alpha);  // sims/reconciliation.pyx:144-145
+            llr[sidx * m.bps + k] = (OUT)v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_g_inv(MapperView m, const double *__restrict__ n_hat,
+                                               const long long *__restrict__ region, int64_t n, int mode,
+                                               double *__restrict__ y_hat)
+{
+    __shared__ SharedTables s;
+    stage_tables(m, s);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t i = (int32_t)region[j];
+        const double target = inv_target(s.sign, s.FYt, s.delta, n_hat[j], i);
+        double cum = 0;
+        for (int k = 0; k < i; ++k) cum += s.p[k];
+        y_hat[j] = (mode & 1) ? g_inv_fast(s.a, s.p, m.order, m.sigma, m.s2, target, 1e-9, i, cum)
+                              : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
+    }
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(256) k_bare_llr(MapperView m, const long long *__restrict__ tx,
+                                                  int64_t n, OUT *__restrict__ llr)
+{
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t i = (int32_t)tx[j];
+        for (int k = 0; k < m.bps; ++k) llr[j * m.bps + k] = (OUT)m.bare[i * m.bps + k];
+    }
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(256) k_direct_llr(MapperView m, const double *__restrict__ y, int64_t n,
+                                                    double two_variance, OUT *__restrict__ llr)
+{
+    __shared__ double a[kMaxOrder];
+    for (int i = threadIdx.x; i < m.order; i += blockDim.x) a[i] = m.constellation[i];
+    __syncthreads();
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        double out[kMaxBps];
+        direct_llr(a, m.order, m.bps, two_variance, y[j], out);
+        for (int k = 0; k < m.bps; ++k) llr[j * m.bps + k] = (OUT)out[k];
+    }
+}
+
+static unsigned grid_for_elems(int64_t n, int per_block = 256, int cap = 148 * 32)
+{
+    int64_t g = (n + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (unsigned)g;
+}
+
+}  // namespace qr
+
+extern "C" {
+
+int qr_mapper_create(int bits_per_symbol, const double *h_constellation, const double *h_thresholds,
+                     const double *h_probabilities, double noise_var, const uint8_t *h_sign_config,
+                     int device, qr_mapper **out)
+{
+    if (!out) return qr::fail(QR_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    if (bits_per_symbol < 1 || bits_per_symbol > qr::kMaxBps)
+        return qr::fail(QR_ERR_INVALID, "bits per symbol must be in 1..8");
+    if (!(noise_var > 0)) return qr::fail(QR_ERR_INVALID, "noise variance must be strictly positive");
+    if (!h_constellation || !h_thresholds || !h_probabilities)
+        return qr::fail(QR_ERR_INVALID, "null alphabet array");
+    if (device < 0) return qr::fail(QR_ERR_INVALID, "the noise mapper needs a CUDA device");
+    qr_mapper *m = new (std::nothrow) qr_mapper();
+    if (!m) return qr::fail(QR_ERR_NOMEM, "out of host memory");
+    const int M = 1 << bits_per_symbol;
+    m->device = device; m->order = M; m->bps = bits_per_symbol;
+    m->noise_var = noise_var;
+    m->sigma = sqrt(noise_var);
+    m->s2 = sqrt(2.0) * m->sigma;
+    qr::DeviceGuard guard(device);
+    auto body = [&]() -> int {
+        const size_t nd = (size_t)M + (M + 1) + M + (M + 1) + M + 3 * (size_t)M * M + (size_t)M * bits_per_symbol;
+        m->n_table_doubles = nd;
+        QR_CUDA_CHECK(cudaMalloc((void **)&m->d_tables, nd * sizeof(double)));
+        QR_CUDA_CHECK(cudaMalloc((void **)&m->d_sign, M));
+        double *p = m->d_tables;
+        m->constellation = p; p += M;
+        m->thresholds = p; p += M + 1;
+        m->probabilities = p; p += M;
+        m->FY_thr = p; p += M + 1;
+        m->delta = p; p += M;
+        m->fwrd = p; p += (size_t)M * M;
+        m->back = p; p += (size_t)M * M;
+        m->inf_erf = p; p += (size_t)M * M;
+        m->bare = p;
+        QR_CUDA_CHECK(cudaMemcpy(m->constellation, h_constellation, M * sizeof(double), cudaMemcpyHostToDevice));
+        QR_CUDA_CHECK(cudaMemcpy(m->thresholds, h_thresholds, (M + 1) * sizeof(double), cudaMemcpyHostToDevice));
+        QR_CUDA_CHECK(cudaMemcpy(m->probabilities, h_probabilities, M * sizeof(double), cudaMemcpyHostToDevice));
+        if (h_sign_config) QR_CUDA_CHECK(cudaMemcpy(m->d_sign, h_sign_config, M, cudaMemcpyHostToDevice));
+        else QR_CUDA_CHECK(cudaMemset(m->d_sign, 0, M));
+        qr::k_mapper_tables<<<1, 32>>>(qr::view_of(m), m->FY_thr, m->delta, m->fwrd, m->back, m->bare, m->inf_erf);
+        QR_CUDA_CHECK(cudaGetLastError());
+        QR_CUDA_CHECK(cudaDeviceSynchronize());
+        return QR_OK;
+    };
+    int rc = body();
+    if (rc != QR_OK) { qr_mapper_destroy(m); return rc; }
+    *out = m;
+    return QR_OK;
+}
+
+void qr_mapper_destroy(qr_mapper *m)
+{
+    if (!m) return;
+    {
+        qr::DeviceGuard guard(m->device);
+        cudaFree(m->d_tables);
+        cudaFree(m->d_sign);
+    }
+    delete m;
+}
+
+int qr_mapper_tables(const qr_mapper *m, double *F_Y_thresholds, double *delta_F_Y, double *fwrd,
+                     double *back, double *bare_llr_table, double *inf_erf_table)
+{
+    if (!m) return qr::fail(QR_ERR_INVALID, "null mapper");
+    qr::DeviceGuard guard(m->device);
+    const int M = m->order;
+    if (F_Y_thresholds) QR_CUDA_CHECK(cudaMemcpy(F_Y_thresholds, m->FY_thr, (M + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+    if (delta_F_Y) QR_CUDA_CHECK(cudaMemcpy(delta_F_Y, m->delta, M * sizeof(double), cudaMemcpyDeviceToHost));
+    if (fwrd) QR_CUDA_CHECK(cudaMemcpy(fwrd, m->fwrd, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToHost));
+    if (back) QR_CUDA_CHECK(cudaMemcpy(back, m->back, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToHost));
+    if (bare_llr_table) QR_CUDA_CHECK(cudaMemcpy(bare_llr_table, m->bare, (size_t)M * m->bps * sizeof(double), cudaMemcpyDeviceToHost));
+    if (inf_erf_table) QR_CUDA_CHECK(cudaMemcpy(inf_erf_table, m->inf_erf, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToHost));
+    return QR_OK;
+}
+
+static int front(const qr_mapper *m, const double *d_y, const int64_t *d_idx_in, int64_t n,
+                 int64_t *d_idx_out, double *d_n_hat, uint8_t *d_bits, void *stream)
+{
+    if (!m) return qr::fail(QR_ERR_INVALID, "null mapper");
+    if (n < 0) return qr::fail(QR_ERR_INVALID, "negative length");
+    if (n == 0) return QR_OK;
+    if ((!d_y && (!d_idx_in || d_n_hat))) return qr::fail(QR_ERR_INVALID, "null sample array");
+    qr::DeviceGuard guard(m->device);
+    qr::k_front_end<<<qr::grid_for_elems(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        qr::view_of(m), d_y, reinterpret_cast<const long long *>(d_idx_in), n,
+        reinterpret_cast<long long *>(d_idx_out), d_n_hat, d_bits);
+    QR_CUDA_CHECK(cudaGetLastError());
+    return QR_OK;
+}
+
+int qr_hard_decide_index(const qr_mapper *m, const double *d_y, int64_t n, int64_t *d_index, void *stream)
+{
+    if (n > 0 && !d_index) return qr::fail(QR_ERR_INVALID, "null output");
+    return front(m, d_y, nullptr, n, d_index, nullptr, nullptr, stream);
+}
+
+int qr_symbols_to_bits(const qr_mapper *m, const int64_t *d_index, int64_t n, uint8_t *d_bits, void *stream)
+{
+    if (n > 0 && (!d_index || !d_bits)) return qr::fail(QR_ERR_INVALID, "null array");
+    return front(m, nullptr, d_index, n, nullptr, nullptr, d_bits, stream);
+}
+
+int qr_map_noise(const qr_mapper *m, const double *d_y, const int64_t *d_index, int64_t n,
+                 double *d_n_hat, void *stream)
+{
+    if (n > 0 && (!d_index || !d_n_hat)) return qr::fail(QR_ERR_INVALID, "null array");
+    return front(m, d_y, d_index, n, nullptr, d_n_hat, nullptr, stream);
+}
+
+int qr_front_end(const qr_mapper *m, const double *d_y, int64_t n, int64_t *d_index, double *d_n_hat,
+                 uint8_t *d_bits, void *stream)
+{
+    return front(m, d_y, nullptr, n, d_index, d_n_hat, d_bits, stream);
+}
+
+int qr_demap_lappr(const qr_mapper *m, const double *d_n_hat, const int64_t *d_tx_index, int64_t n,
+                   int mode, double alpha, void *d_llr, int llr_dtype, void *stream)
+{
+    if (!m) return qr::fail(QR_ERR_INVALID, "null mapper");
+    if (n < 0) return qr::fail(QR_ERR_INVALID, "negative length");
+    if (llr_dtype != QR_F32 && llr_dtype != QR_F64) return qr::fail(QR_ERR_INVALID, "bad llr dtype");
+    if (mode < 0 || mode > 3) return qr::fail(QR_ERR_INVALID, "bad demap mode");
+    if (n == 0) return QR_OK;
+    if (!d_n_hat || !d_tx_index || !d_llr) return qr::fail(QR_ERR_INVALID, "null array");
+    qr::DeviceGuard guard(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = qr::grid_for_elems(n, 128, 148 * 64);
+    if (llr_dtype == QR_F64)
+        qr::k_demap<double><<<grid, 128, 0, st>>>(qr::view_of(m), d_n_hat, reinterpret_cast<const long long *>(d_tx_index),
+                                                   n, mode, alpha, static_cast<double *>(d_llr));
+    else
+        qr::k_demap<float><<<grid, 128, 0, st>>>(qr::view_of(m), d_n_hat, reinterpret_cast<const long long *>(d_tx_index),
+                                                  n, mode, alpha, static_cast<float *>(d_llr));
+    QR_CUDA_CHECK(cudaGetLastError());
+    return QR_OK;
+}
+
+int qr_g_inv_search(const qr_mapper *m, const double *d_n_hat, const int64_t *d_region, int64_t n,
+                    int mode, double *d_y_hat, void *stream)
+{
+    if (!m) return qr::fail(QR_ERR_INVALID, "null mapper");
+    if (n < 0) return qr::fail(QR_ERR_INVALID, "negative length");
+    if (n == 0) return QR_OK;
+    if (!d_n_hat || !d_region || !d_y_hat) return qr::fail(QR_ERR_INVALID, "null array");
+    qr::DeviceGuard guard(m->device);
+    qr::k_g_inv<<<qr::grid_for_elems(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        qr::view_of(m), d_n_hat, reinterpret_cast<const long long *>(d_region), n, mode, d_y_hat);
+    QR_CUDA_CHECK(cudaGetLastError());
+    return QR_OK;
+}
+
+int qr_bare_llr(const qr_mapper *m, const int64_t *d_tx_index, int64_t n, void *d_llr, int llr_dtype,
+                void *stream)
+{
+    if (!m) return qr::fail(QR_ERR_INVALID, "null mapper");
+    if (n < 0) return qr::fail(QR_ERR_INVALID, "negative length");
+    if (llr_dtype != QR_F32 && llr_dtype != QR_F64) return qr::fail(QR_ERR_INVALID, "bad llr dtype");
+    if (n == 0) return QR_OK;
+    if (!d_tx_index || !d_llr) return qr::fail(QR_ERR_INVALID, "null array");
+    qr::DeviceGuard guard(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (llr_dtype == QR_F64)
+        qr::k_bare_llr<double><<<qr::grid_for_elems(n), 256, 0, st>>>(qr::view_of(m), reinterpret_cast<const long long *>(d_tx_index), n, static_cast<double *>(d_llr));
+    else
+        qr::k_bare_llr<float><<<qr::grid_for_elems(n), 256, 0, st>>>(qr::view_of(m), reinterpret_cast<const long long *>(d_tx_index), n, static_cast<float *>(d_llr));
+    QR_CUDA_CHECK(cudaGetLastError());
+    return QR_OK;
+}
+
+int qr_direct_llr(const qr_mapper *m, const double *d_y, int64_t n, double two_variance, void *d_llr,
+                  int llr_dtype, void *stream)
+{
+    if (!m) return qr::fail(QR_ERR_INVALID, "null mapper");
+    if (n < 0) return qr::fail(QR_ERR_INVALID, "negative length");
+    if (llr_dtype != QR_F32 && llr_dtype != QR_F64) return qr::fail(QR_ERR_INVALID, "bad llr dtype");
+    if (n == 0) return QR_OK;
+    if (!d_y || !d_llr) return qr::fail(QR_ERR_INVALID, "null array");
+    qr::DeviceGuard guard(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (llr_dtype == QR_F64)
+        qr::k_direct_llr<double><<<qr::grid_for_elems(n), 256, 0, st>>>(qr::view_of(m), d_y, n, two_variance, static_cast<double *>(d_llr));
+    else
+        qr::k_direct_llr<float><<<qr::grid_for_elems(n), 256, 0, st>>>(qr::view_of(m), d_y, n, two_variance, static_cast<float *>(d_llr));
+    QR_CUDA_CHECK(cudaGetLastError());
+    return QR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+// Per-symbol arithmetic of the softening noise mapper / LLR demapper, fp64
+// (reference: qamreconciliation/noisemapper.pyx, alphabet.pyx:98-107, sims/reconciliation.pyx:25-51).
+// __host__ __device__ so tests/emu can run the same code on the CPU.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+
+#include "qr_common.h"
+
+namespace qr {
+
+constexpr int kMaxBps = 8;
+constexpr int kMaxOrder = 1 << kMaxBps;
+
+// What a kernel needs of the mapper, by value (pointers are device pointers).
+struct MapperView {
+    int32_t order, bps;
+    double noise_var, sigma, s2;  // s2 = sqrt(2) * sigma, as at noisemapper.pyx:66-67
+    const double *constellation;  // [order]
+    const double *thresholds;     // [order+1]
+    const double *probabilities;  // [order]
+    const uint8_t *sign_config;   // [order]
+    const double *FY_thr;         // [order+1]  F_Y_thresholds
+    const double *delta;          // [order]    delta_F_Y
+    const double *bare;           // [order*bps]
+};
+
+// rounding-exact multiply/add: the reference is compiled without FMA contraction
+QR_HD double mul_rn(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+QR_HD double add_rn(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+
+// __F_Z (noisemapper.pyx:66-67)
+QR_HD double gauss_cdf(double z, double mu, double s2)
+{
+    return 0.5 * (1 + erf((z - mu) / s2));
+}
+
+// _single_F_Y (noisemapper.pyx:278-286): mixture CDF, summed k = 0 upward
+QR_HD double mixture_cdf(const double *a, const double *p, int order, double s2, double y)
+{
+    double res = mul_rn(gauss_cdf(y, a[0], s2), p[0]);
+    for (int i = 1; i < order; ++i) res = add_rn(res, mul_rn(gauss_cdf(y, a[i], s2), p[i]));
+    return res;
+}
+
+// mixture pdf (derivative of the above), for the Newton solver
+QR_HD double mixture_pdf(const double *a, const double *p, int order, double sigma, double y)
+{
+    double res = 0;
+    for (int i = 0; i < order; ++i) {
+        const double z = (y - a[i]) / sigma;
+        res += p[i] * exp(-0.5 * z * z);
+    }
+    return res * (0.3989422804014327 / sigma);
+}
+
+// __binsearch (noisemapper.pyx:27-44) on an (offset, length) window instead of array slices;
+// the comparisons come in the same order, so NaN and out-of-range inputs resolve identically.
+QR_HD int32_t region_search(const double *dom, int32_t len, double val)
+{
+    int32_t base = 0;
+    for (;;) {
+        if (len == 1) return base;
+        if (val < dom[0]) return base;
+        if (val > dom[len - 1]) return base + len - 1;
+        const int32_t mid = len / 2 - 1;
+        if (val < dom[mid]) { len = mid; continue; }
+        if (val >= dom[mid + 1]) { base += mid + 1; dom += mid + 1; len -= mid + 1; continue; }
+        return base + mid;
+    }
+}
+
+// hard_decide_index (noisemapper.pyx:349-359)
+QR_HD int32_t hard_decide(const double *thresholds, int order, double y)
+{
+    int32_t r = region_search(thresholds, order + 1, y);
+    return r == order ? order - 1 : r;
+}
+
+// Gray bit k of symbol i (bicm.pyx:26-41; closed form as at noisemapper.pyx:208-215)
+QR_HD uint8_t gray_bit(int32_t i, int k)
+{
+    const int32_t q = i >> k;
+    return (uint8_t)(((q * (q + 1)) & 3) != 0);
+}
+
+// g (noisemapper.pyx:289-292)
+QR_HD double soften(const MapperView &m, const double *FYt, const double *delta, double F, int32_t i)
+{
+    return m.sign_config[i] ? (FYt[i + 1] - F) / delta[i] : (F - FYt[i]) / delta[i];
+}
+
+QR_HD double inv_target(const uint8_t *sign_config, const double *FYt, const double *delta, double n_hat,
+                        int32_t i)
+{
+    // noisemapper.pyx:314-317
+    return sign_config[i] ? add_rn(FYt[i + 1], -mul_rn(n_hat, delta[i]))
+                          : add_rn(mul_rn(n_hat, delta[i]), FYt[i]);
+}
+
+constexpr int kMaxDoublings = 1100;  // 2^1100 overflows to inf: the reference would spin forever
+constexpr int kMaxHalvings = 1200;
+
+struct Bracket {
+    double lo, hi;
+    double f_end;  // F at the end the doubling loop last evaluated
+};
+
+// the doubling part of g_inv_search (noisemapper.pyx:319-334)
+QR_HD Bracket bracket_root(const double *a, const double *p, int order, double s2, double target)
+{
+    Bracket b;
+    if (target > .5) {
+        b.hi = 1; b.lo = 0;
+        b.f_end = mixture_cdf(a, p, order, s2, b.hi);
+        for (int it = 0; b.f_end < target && it < kMaxDoublings; ++it) {
+            b.lo = b.hi;
+            b.hi *= 2.;
+            b.f_end = mixture_cdf(a, p, order, s2, b.hi);
+        }
+    } else {
+        b.lo = -1; b.hi = 0;
+        b.f_end = mixture_cdf(a, p, order, s2, b.lo);
+        for (int it = 0; b.f_end > target && it < kMaxDoublings; ++it) {
+            b.hi = b.lo;
+            b.lo *= 2.;
+            b.f_end = mixture_cdf(a, p, order, s2, b.lo);
+        }
+    }
+    return b;
+}
+
+// g_inv_search (noisemapper.pyx:310-345), exact replay: bisect on F until the bracket is <= 1e-9
+QR_HD double g_inv_exact(const double *a, const double *p, int order, double s2, double target,
+                         double accuracy)
+{
+    Bracket b = bracket_root(a, p, order, s2, target);
+    double lo = b.lo, hi = b.hi;
+    for (int it = 0; (hi - lo) > accuracy && it < kMaxHalvings; ++it) {
+        const double mid = (hi + lo) / 2;
+        if (mixture_cdf(a, p, order, s2, mid) > target) hi = mid;
+        else lo = mid;
+    }
+    return (hi + lo) / 2;
+}
+
+// Acklam's rational approximation of the standard normal quantile (|rel err| < 1.2e-9); only a
+// starting point for Newton, so the accuracy is ample.
+QR_HD double norm_quantile(double q)
+{
+    const double a1 = -3.969683028665376e+01, a2 = 2.209460984245205e+02, a3 = -2.759285104469687e+02,
+                 a4 = 1.383577518672690e+02, a5 = -3.066479806614716e+01, a6 = 2.506628277459239e+00;
+    const double b1 = -5.447609879822406e+01, b2 = 1.615858368580409e+02, b3 = -1.556989798598866e+02,
+                 b4 = 6.680131188771972e+01, b5 = -1.328068155288572e+01;
+    const double c1 = -7.784894002430293e-03, c2 = -3.223964580411365e-01, c3 = -2.400758277161838e+00,
+                 c4 = -2.549732539343734e+00, c5 = 4.374664141464968e+00, c6 = 2.938163982698783e+00;
+    const double d1 = 7.784695709041462e-03, d2 = 3.224671290700398e-01, d3 = 2.445134137142996e+00,
+                 d4 = 3.754408661907416e+00;
+    if (q < 0.02425) {
+        const double t = sqrt(-2 * log(q));
+        return (((((c1 * t + c2) * t + c3) * t + c4) * t + c5) * t + c6) /
+               ((((d1 * t + d2) * t + d3) * t + d4) * t + 1);
+    }
+    if (q > 1 - 0.02425) {
+        const double t = sqrt(-2 * log(1 - q));
+        return -(((((c1 * t + c2) * t + c3) * t + c4) * t + c5) * t + c6) /
+               ((((d1 * t + d2) * t + d3) * t + d4) * t + 1);
+    }
+    const double t = q - 0.5, r = t * t;
+    return (((((a1 * r + a2) * r + a3) * r + a4) * r + a5) * r + a6) * t /
+           (((((b1 * r + b2) * r + b3) * r + b4) * r + b5) * r + 1);
+}
+
+// Fast variant of g_inv_search.  The bisection's outcome is a function of the root y* alone (F is
+// monotone: F(mid) > target  <=>  mid > y*), so: same bracket as the reference, a safeguarded
+// Newton iteration for y* (a handful of F evaluations instead of ~35), then the reference's
+// halving sequence replayed with comparisons against y* -- no F evaluations -- which lands in the
+// same 1e-9 cell and returns the same midpoint unless y* is within the Newton error of a midpoint.
+QR_HD double g_inv_fast(const double *a, const double *p, int order, double sigma, double s2,
+                        double target, double accuracy, int32_t region, double cum_below)
+{
+    Bracket b = bracket_root(a, p, order, s2, target);
+    double lo = b.lo, hi = b.hi;
+    double root;
+    // degenerate ends: F never rises above (or falls below) the target inside the bracket
+    const bool upper = target > .5;
+    if (upper && !(b.f_end > target)) {
+        root = hi;               // F(hi) == target (plateau or exact hit): every midpoint goes to lo
+    } else if (!upper && b.f_end > target) {
+        root = lo;               // doubling gave up (cannot happen for target >= 0)
+    } else {
+        // invariant: F(rlo) <= target < F(rhi)
+        double rlo = lo, rhi = hi;
+        if (!upper && mixture_cdf(a, p, order, s2, hi) <= target) {
+            root = hi;           // F(0) <= target <= .5: the reference walks up to hi as well
+        } else {
+            // start from the quantile of the region's own Gaussian
+            double q = (target - cum_below) / p[region];
+            q = q < 1e-300 ? 1e-300 : (q > 1 - 1e-16 ? 1 - 1e-16 : q);
+            double y = a[region] + sigma * norm_quantile(q);
+            if (!(y > rlo && y < rhi)) y = 0.5 * (rlo + rhi);
+            root = y;
+            for (int it = 0; it < 200; ++it) {
+                const double F = mixture_cdf(a, p, order, s2, y);
+                if (F > target) rhi = y; else rlo = y;
+                const double f = mixture_pdf(a, p, order, sigma, y);
+                double yn = y - (F - target) / f;
+                if (!(yn > rlo && yn < rhi)) yn = 0.5 * (rlo + rhi);   // Newton left the bracket
+                const double step = fabs(yn - y);
+                y = yn;
+                root = y;
+                if (step <= 4e-16 * fmax(1.0, fabs(y)) || (rhi - rlo) <= 1e-15 * fmax(1.0, fabs(y))) break;
+            }
+            // settle on the side the comparisons imply: root = sup{ y : F(y) <= target }
+        }
+    }
+    for (int it = 0; (hi - lo) > accuracy && it < kMaxHalvings; ++it) {
+        const double mid = (hi + lo) / 2;
+        if (mid > root) hi = mid;
+        else lo = mid;
+    }
+    return (hi + lo) / 2;
+}
+
+// demap_lappr (noisemapper.pyx:450-540) given the `order` reconstructed samples y_hat[i].
+// NOTE the reference divides the exponent by 2*sigma^2 only for k > j (:511-515), not for k < j
+// (:503-507); `corrected` divides in both.
+QR_HD void demap_from_yhat(const double *a, const double *p, const double *delta, int order, int bps,
+                           double two_s2, const double *y_hat, int32_t j, bool corrected, double *lappr)
+{
+    double N[kMaxBps], D[kMaxBps];
+    for (int k = 0; k < bps; ++k) { N[k] = 0; D[k] = 0; }
+    for (int i = 0; i < order; ++i) {
+        const double yh = y_hat[i];
+        double s = 0;
+        for (int k = 0; k < j; ++k) {
+            double ex = mul_rn(add_rn(add_rn(mul_rn(2, yh), -a[k]), -a[j]), add_rn(a[k], -a[j]));
+            if (corrected) ex = ex / two_s2;
+            s = add_rn(s, mul_rn(exp(ex), p[k]));
+        }
+        s = add_rn(s, p[j]);
+        for (int k = j + 1; k < order; ++k) {
+            const double ex = mul_rn(add_rn(add_rn(mul_rn(2, yh), -a[k]), -a[j]), add_rn(a[k], -a[j])) / two_s2;
+            s = add_rn(s, mul_rn(exp(ex), p[k]));
+        }
+        const double w = delta[i] / s;
+        int q = i;
+        for (int k = 0; k < bps; ++k) {
+            if ((q * (q + 1)) & 3) D[k] = add_rn(D[k], w);
+            else N[k] = add_rn(N[k], w);
+            q >>= 1;
+        }
+    }
+    for (int k = 0; k < bps; ++k) lappr[k] = log(N[k]) - log(D[k]);
+}
+
+// direct-reconciliation LLR (sims/reconciliation.pyx:25-51)
+QR_HD void direct_llr(const double *a, int order, int bps, double two_variance, double y, double *lappr)
+{
+    double N[kMaxBps], D[kMaxBps];
+    for (int l = 0; l < bps; ++l) { N[l] = 0; D[l] = 0; }
+    for (int i = 0; i < order; ++i) {
+        const double d = y - a[i];
+        const double term = exp(-mul_rn(d, d) / two_variance);
+        int q = i;
+        for (int l = 0; l < bps; ++l) {
+            if ((q * (q + 1)) & 3) D[l] = add_rn(D[l], term);
+            else N[l] = add_rn(N[l], term);
+            q >>= 1;
+        }
+    }
+    for (int l = 0; l < bps; ++l) lappr[l] = log(N[l]) - log(D[l]);
+}
+
+}  // namespace qr

@@ -1,0 +1,121 @@
+// Whole reverse-reconciliation pass over host buffers: the chain of the reference's Monte-Carlo
+// loop body (sims/reconciliation.pyx:129-153 soft reverse, :300-308 hard reverse, :214-227 direct)
+// for a batch of frames, host -> device -> host inside one call.
+#include <cuda_runtime.h>
+
+#include <cstring>
+
+#include "qr_handles.h"
+
+namespace {
+
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base(static_cast<char *>(b)) {}
+    template <typename T>
+    T *take(size_t count)
+    {
+        off = (off + 255) / 256 * 256;
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct Buffers {
+    double *y, *n_hat;
+    int64_t *tx, *idx;
+    uint8_t *word, *synd, *success;
+    void *llr, *post;
+    int32_t *iters, *errors;
+};
+
+Buffers carve(Carver &c, int64_t frames, int64_t S, int64_t N, int64_t C, size_t wl, size_t wp)
+{
+    Buffers b;
+    b.y = c.take<double>(frames * S);
+    b.n_hat = c.take<double>(frames * S);
+    b.tx = c.take<int64_t>(frames * S);
+    b.idx = c.take<int64_t>(frames * S);
+    b.word = c.take<uint8_t>(frames * N);
+    b.synd = c.take<uint8_t>(frames * C);
+    b.success = c.take<uint8_t>(frames);
+    b.llr = c.take<char>(frames * N * wl);
+    b.post = c.take<char>(frames * N * wp);
+    b.iters = c.take<int32_t>(frames);
+    b.errors = c.take<int32_t>(frames);
+    return b;
+}
+
+}  // namespace
+
+extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha,
+                                 const double *h_y, const int64_t *h_tx_index, int64_t frames,
+                                 int32_t max_iterations, int64_t k_info, uint8_t *h_success,
+                                 int32_t *h_iters, void *h_post, int post_dtype, uint8_t *h_word,
+                                 int32_t *h_bit_errors, void *stream_)
+{
+    if (!d || !m) return qr::fail(QR_ERR_INVALID, "null handle");
+    if (mode < 0 || mode > 2) return qr::fail(QR_ERR_INVALID, "reconciliation mode must be 0, 1 or 2");
+    if (frames < 0) return qr::fail(QR_ERR_INVALID, "bad frame count");
+    if (d->device != m->device) return qr::fail(QR_ERR_INVALID, "decoder and mapper live on different devices");
+    const qr_graph *g = d->g;
+    const int64_t N = g->N, C = g->C;
+    if (N % m->bps) return qr::fail(QR_ERR_INVALID, "codeword length is not a multiple of bits per symbol");
+    if (k_info < 0 || k_info > N) return qr::fail(QR_ERR_INVALID, "bad information length");
+    if (h_post && post_dtype != QR_F32 && post_dtype != QR_F64) return qr::fail(QR_ERR_INVALID, "bad dtype");
+    if (frames == 0) return QR_OK;
+    if (!h_y || !h_tx_index) return qr::fail(QR_ERR_INVALID, "null input array");
+    const int64_t S = N / m->bps;
+    const int llr_dtype = d->precision == QR_F64 ? QR_F64 : QR_F32;
+    const size_t wl = llr_dtype == QR_F64 ? 8 : 4;
+    if (!h_post) post_dtype = llr_dtype;
+    const size_t wp = post_dtype == QR_F64 ? 8 : 4;
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    qr::DeviceGuard guard(d->device);
+
+    Carver sizing(nullptr);
+    carve(sizing, frames, S, N, C, wl, wp);
+    const size_t need = sizing.off + 256;
+    if (need > d->pipe_cap) {
+        QR_CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(d->pipe_buf);
+        d->pipe_buf = nullptr;
+        d->pipe_cap = 0;
+        QR_CUDA_CHECK(cudaMalloc(&d->pipe_buf, need));
+        d->pipe_cap = need;
+    }
+    Carver c(d->pipe_buf);
+    Buffers b = carve(c, frames, S, N, C, wl, wp);
+
+    QR_CUDA_CHECK(cudaMemcpyAsync(b.y, h_y, frames * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    QR_CUDA_CHECK(cudaMemcpyAsync(b.tx, h_tx_index, frames * S * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    int rc;
+    if (mode == 0) {
+        if ((rc = qr_front_end(m, b.y, frames * S, b.idx, b.n_hat, b.word, st))) return rc;
+        if ((rc = qr_eval_syndrome(g, b.word, b.synd, frames, st))) return rc;
+        if ((rc = qr_demap_lappr(m, b.n_hat, b.tx, frames * S, demap_mode, alpha, b.llr, llr_dtype, st))) return rc;
+    } else if (mode == 1) {
+        if ((rc = qr_front_end(m, b.y, frames * S, b.idx, nullptr, b.word, st))) return rc;
+        if ((rc = qr_eval_syndrome(g, b.word, b.synd, frames, st))) return rc;
+        if ((rc = qr_bare_llr(m, b.tx, frames * S, b.llr, llr_dtype, st))) return rc;
+    } else {
+        if ((rc = qr_symbols_to_bits(m, b.tx, frames * S, b.word, st))) return rc;
+        if ((rc = qr_eval_syndrome(g, b.word, b.synd, frames, st))) return rc;
+        if ((rc = qr_direct_llr(m, b.y, frames * S, 2 * m->noise_var, b.llr, llr_dtype, st))) return rc;
+    }
+    if ((rc = qr_decode_batch(d, b.llr, llr_dtype, b.synd, frames, max_iterations, b.success, b.iters, b.post,
+                              post_dtype, st)))
+        return rc;
+    if (h_bit_errors) {
+        if ((rc = qr_count_errors(b.post, post_dtype, b.word, frames, N, k_info, b.errors, st))) return rc;
+        QR_CUDA_CHECK(cudaMemcpyAsync(h_bit_errors, b.errors, frames * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (h_success) QR_CUDA_CHECK(cudaMemcpyAsync(h_success, b.success, frames, cudaMemcpyDeviceToHost, st));
+    if (h_iters) QR_CUDA_CHECK(cudaMemcpyAsync(h_iters, b.iters, frames * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (h_post) QR_CUDA_CHECK(cudaMemcpyAsync(h_post, b.post, frames * N * wp, cudaMemcpyDeviceToHost, st));
+    if (h_word) QR_CUDA_CHECK(cudaMemcpyAsync(h_word, b.word, frames * N, cudaMemcpyDeviceToHost, st));
+    QR_CUDA_CHECK(cudaStreamSynchronize(st));
+    return QR_OK;
+}

@@ -1,0 +1,67 @@
+"""Batched reverse-reconciliation pass: the body of the reference's Monte-Carlo loop
+(sims/reconciliation.pyx:129-153 soft reverse, :300-308 hard reverse, :214-227 soft direct) for a
+whole batch of frames at once."""
+import torch
+
+from . import _abi
+from ._util import stream, to_dev
+
+SOFT_REVERSE, HARD_REVERSE, SOFT_DIRECT = 0, 1, 2
+
+
+class Reconciler:
+    """Binds a Decoder, a Matrix-equivalent graph and a NoiseMapper for one SNR point."""
+
+    def __init__(self, dec, nm, mode=SOFT_REVERSE, precision="fp32", demap="fast", alpha=1.0, lanes=None,
+                 schedule=None):
+        if dec.vnum % nm.bit_per_symbol:
+            raise ValueError(f"codeword length {dec.vnum} is not a multiple of bits per symbol {nm.bit_per_symbol}")
+        self.dec, self.nm, self.mode, self.alpha = dec, nm, mode, float(alpha)
+        self.precision = precision
+        self.prec_code = {"fp32": _abi.QR_F32, "fp64": _abi.QR_F64}[precision]
+        self.llr_dtype = torch.float32 if precision == "fp32" else torch.float64
+        from .noisemapper import _demap_mode
+        self.demap_code = _demap_mode(demap)
+        self.lanes, self.schedule = lanes, schedule
+        self.N, self.C = dec.vnum, dec.cnum
+        self.S = self.N // nm.bit_per_symbol
+
+    def run_device(self, y, x, max_iterations, k_info=None, want_post=True):
+        """y [B, S] float64 and x [B, S] int64 already on the GPU.  Returns a dict of CUDA tensors:
+        success, iters, post (or None), word, synd, bit_errors (int32 per frame over the first k_info bits)."""
+        from . import utils
+        nm, dec = self.nm, self.dec
+        B = y.shape[0]
+        if self.mode == SOFT_DIRECT:
+            word = nm._pa.demap_symbols_to_bits_batch(x)
+            llr = nm.direct_llr_batch(y, out_dtype=self.llr_dtype)
+        elif self.mode == HARD_REVERSE:
+            _, _, word = nm.front_end_batch(y, want_index=False, want_noise=False)
+            llr = nm.bare_llr_batch(x, out_dtype=self.llr_dtype)
+        else:
+            _, n_hat, word = nm.front_end_batch(y, want_index=False)
+            llr = nm.demap_lappr_array_batch(n_hat, x, mode=self.demap_code, alpha=self.alpha, out_dtype=self.llr_dtype)
+        synd = torch.empty((B, self.C), dtype=torch.uint8, device=y.device)
+        _abi.check(_abi.lib().qr_eval_syndrome(dec._g.h, word.data_ptr(), synd.data_ptr(), B, stream()))
+        ok, it, post = dec.decode_batch(llr, synd, max_iterations, precision=self.precision, lanes=self.lanes,
+                                        schedule=self.schedule, out_dtype=self.llr_dtype, return_post=True)
+        errs = utils.count_errors_batch(post, word, k=k_info) if k_info is not None else None
+        return dict(success=ok, iters=it, post=post if want_post else None, word=word, synd=synd, bit_errors=errs,
+                    llr=llr)
+
+    def run_host(self, y, x, max_iterations, k_info, out):
+        """Host buffers in, host buffers out, through qr_reconcile_host (copies inside the call).
+        y: float64 [B, S], x: int64 [B, S] CPU tensors (pinned for asynchronous copies); `out` is a dict of
+        preallocated CPU tensors: success uint8[B], iters int32[B], bit_errors int32[B], optional post [B, N]
+        and word uint8[B, N]."""
+        B = y.shape[0]
+        post = out.get("post")
+        word = out.get("word")
+        h = self.dec._handle(self.prec_code, self.lanes, self.schedule)
+        _abi.check(_abi.lib().qr_reconcile_host(
+            h, self.nm._h, self.mode, self.demap_code, self.alpha, y.data_ptr(), x.data_ptr(), B,
+            int(max_iterations), int(k_info), out["success"].data_ptr(), out["iters"].data_ptr(),
+            post.data_ptr() if post is not None else None,
+            (_abi.QR_F64 if post.dtype == torch.float64 else _abi.QR_F32) if post is not None else _abi.QR_F32,
+            word.data_ptr() if word is not None else None, out["bit_errors"].data_ptr(), stream()))
+        return out

@@ -1,0 +1,188 @@
+// CPU EMULATION HARNESS -- test infrastructure only, never loaded by the product package.
+//
+// Compiles the product's __host__ __device__ work-item functions (csrc/qr_decode_core.cuh,
+// csrc/qr_mapper_core.cuh) with g++ and drives them with plain loops in place of the CUDA
+// grid, so the lane state machine, the index arithmetic and the host-side math can be checked
+// against the oracle in the container that has no GPU.  It says nothing about launch
+// configuration, barriers or memory ordering: those are covered by the -m gpu tests.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../qam-reconciliation_b200/csrc/qr_common.h"
+#include "../../qam-reconciliation_b200/csrc/qr_graph_build.h"
+#include "../../qam-reconciliation_b200/csrc/qr_decode_core.cuh"
+#include "../../qam-reconciliation_b200/csrc/qr_mapper_core.cuh"
+
+namespace qr {
+static std::string g_err;
+void set_error(const std::string &m) { g_err = m; }
+int fail(int code, const std::string &m) { g_err = m; return code; }
+}  // namespace qr
+
+using namespace qr;
+
+template <typename T, int VEC, int D>
+static uint32_t emu_bin(const DecodeParams<T> &P, const LaneInfo<VEC> &L, const CheckBin &bin)
+{
+    uint32_t bad = 0;
+    for (int32_t k = 0; k < bin.count; ++k)
+        bad |= check_item<T, VEC, D>(P, L, bin.chk_begin + k, bin.slot_begin + k * bin.degree, bin.degree);
+    return bad;
+}
+
+template <typename T, int VEC>
+static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *llr, int llr_dtype,
+                        const uint8_t *synd, int64_t frames, int maxiter, uint8_t *success, int32_t *iters,
+                        void *post, int post_dtype, int64_t *steps_out)
+{
+    std::vector<T> c2v((size_t)g.E * lanes), postw((size_t)g.N * lanes), llrw((size_t)g.N * lanes);
+    std::vector<uint8_t> syndw((size_t)g.C * lanes);
+    std::vector<LaneState> st(2 * lanes);
+    std::vector<int32_t> unsat(2 * lanes, 0), ctrl(CTRL_WORDS, 0);
+    unsigned long long stats[2] = {0, 0};
+    // poison the workspace: nothing may depend on its initial contents
+    for (auto &v : c2v) v = (T)1e30;
+    for (auto &v : postw) v = (T)-7e29;
+    for (auto &v : llrw) v = (T)3e29;
+    DecodeParams<T> P;
+    P.bins = g.bins.data(); P.n_bins = (int32_t)g.bins.size();
+    P.chk_order = g.chk_order.data(); P.slot_var = g.slot_var.data();
+    P.var_ptr = g.var_ptr.data(); P.var_slot = g.var_slot.data();
+    P.N = g.N; P.C = g.C; P.E = g.E; P.lanes = lanes;
+    P.c2v = c2v.data(); P.post = postw.data(); P.llr = llrw.data(); P.synd = syndw.data();
+    P.st[0] = st.data(); P.st[1] = st.data() + lanes;
+    P.unsat[0] = unsat.data(); P.unsat[1] = unsat.data() + lanes;
+    P.llr_in = llr; P.llr_in_f64 = llr_dtype == QR_F64; P.synd_in = synd;
+    P.frames = frames; P.maxiter = maxiter; P.success = success; P.iters = iters;
+    P.post_out = post; P.post_out_f64 = post_dtype == QR_F64;
+    P.ctrl = ctrl.data(); P.stats = stats;
+    for (int l = 0; l < lanes; ++l) {
+        LaneState s;
+        s.frame = l < frames ? l : -1; s.iter = 0; s.fresh = s.frame >= 0; s.pad = 0;
+        st[l] = s; st[lanes + l] = s;
+    }
+    ctrl[CTRL_NEXT_FRAME] = (int32_t)std::min<int64_t>(lanes, frames);
+    ctrl[CTRL_REMAINING] = (int32_t)frames;
+    const int LV = lanes / VEC;
+    int64_t step = 0;
+    for (; ctrl[CTRL_REMAINING] > 0; ++step) {
+        if (step > (frames + lanes) * (int64_t)(maxiter + 3)) return -1;  // runaway guard
+        const int cur = step & 1;
+        for (int jv = 0; jv < LV; ++jv) {
+            LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
+            if (!L.active) continue;
+            uint32_t bad = 0;
+            for (const CheckBin &bin : g.bins) {
+                if (generic) { bad |= emu_bin<T, VEC, 0>(P, L, bin); continue; }
+                switch (bin.degree) {
+                case 2: bad |= emu_bin<T, VEC, 2>(P, L, bin); break;
+                case 3: bad |= emu_bin<T, VEC, 3>(P, L, bin); break;
+                case 4: bad |= emu_bin<T, VEC, 4>(P, L, bin); break;
+                case 5: bad |= emu_bin<T, VEC, 5>(P, L, bin); break;
+                case 6: bad |= emu_bin<T, VEC, 6>(P, L, bin); break;
+                case 7: bad |= emu_bin<T, VEC, 7>(P, L, bin); break;
+                case 8: bad |= emu_bin<T, VEC, 8>(P, L, bin); break;
+                default: bad |= emu_bin<T, VEC, 0>(P, L, bin); break;
+                }
+            }
+            for (int k = 0; k < VEC; ++k)
+                if (bad >> k & 1) P.unsat[cur][L.l0 + k] = 1;
+        }
+        for (int jv = 0; jv < LV; ++jv) {
+            LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
+            decide_lanes<T, VEC>(P, cur, L);
+            if (L.upd | L.fin_ok | L.fin_fail)
+                for (int32_t n = 0; n < g.N; ++n) var_item<T, VEC>(P, L, n);
+            bookkeep_lanes<T, VEC>(P, cur, L);
+        }
+    }
+    if (steps_out) *steps_out = step;
+    return 0;
+}
+
+extern "C" {
+
+const char *emu_last_error() { return qr::g_err.c_str(); }
+
+int emu_graph_tables(const int64_t *vid, const int64_t *cid, int64_t E, int64_t *dims, int32_t *chk_order,
+                     int32_t *slot_edge, int32_t *slot_var, int32_t *var_ptr, int32_t *var_slot)
+{
+    qr_graph g;
+    int rc = build_host_tables(g, vid, cid, E);
+    if (rc) return rc;
+    dims[0] = g.N; dims[1] = g.C; dims[2] = g.E; dims[3] = g.max_cdeg; dims[4] = g.max_vdeg;
+    dims[5] = (int64_t)g.bins.size();
+    if (chk_order) memcpy(chk_order, g.chk_order.data(), g.C * 4);
+    if (slot_edge) memcpy(slot_edge, g.slot_edge.data(), g.E * 4);
+    if (slot_var) memcpy(slot_var, g.slot_var.data(), g.E * 4);
+    if (var_ptr) memcpy(var_ptr, g.var_ptr.data(), (g.N + 1) * 4);
+    if (var_slot) memcpy(var_slot, g.var_slot.data(), g.E * 4);
+    return 0;
+}
+
+int emu_decode(const int64_t *vid, const int64_t *cid, int64_t E, int precision, int lanes, int generic,
+               const void *llr, int llr_dtype, const uint8_t *synd, int64_t frames, int maxiter,
+               uint8_t *success, int32_t *iters, void *post, int post_dtype, int64_t *steps)
+{
+    qr_graph g;
+    int rc = build_host_tables(g, vid, cid, E);
+    if (rc) return rc;
+    if (precision == QR_F64)
+        return emu_decode_t<double, 2>(g, lanes, generic != 0, llr, llr_dtype, synd, frames, maxiter, success,
+                                       iters, post, post_dtype, steps);
+    return emu_decode_t<float, 4>(g, lanes, generic != 0, llr, llr_dtype, synd, frames, maxiter, success, iters,
+                                  post, post_dtype, steps);
+}
+
+// mapper arithmetic: mode bit 0 = fast inverse, bit 1 = corrected exponent
+void emu_demap(int bps, const double *a, const double *thr, const double *p, double noise_var,
+               const uint8_t *sign, const double *n_hat, const int64_t *tx, int64_t n, int mode, double *llr,
+               double *yhat_out)
+{
+    const int M = 1 << bps;
+    const double sigma = sqrt(noise_var), s2 = sqrt(2.0) * sigma;
+    std::vector<double> FYt(M + 1), delta(M);
+    FYt[0] = 0; FYt[M] = 1;
+    for (int i = 1; i < M; ++i) FYt[i] = mixture_cdf(a, p, M, s2, thr[i]);
+    for (int i = 0; i < M; ++i) delta[i] = FYt[i + 1] - FYt[i];
+    std::vector<double> yh(M);
+    for (int64_t s = 0; s < n; ++s) {
+        double cum = 0;
+        for (int i = 0; i < M; ++i) {
+            const double target = inv_target(sign, FYt.data(), delta.data(), n_hat[s], i);
+            yh[i] = (mode & 1) ? g_inv_fast(a, p, M, sigma, s2, target, 1e-9, i, cum)
+                               : g_inv_exact(a, p, M, s2, target, 1e-9);
+            cum += p[i];
+            if (yhat_out) yhat_out[s * M + i] = yh[i];
+        }
+        demap_from_yhat(a, p, delta.data(), M, bps, 2 * noise_var, yh.data(), (int32_t)tx[s], (mode & 2) != 0,
+                        llr + s * bps);
+    }
+}
+
+void emu_front(int bps, const double *a, const double *thr, const double *p, double noise_var,
+               const uint8_t *sign, const double *y, int64_t n, int64_t *idx, double *n_hat, uint8_t *bits)
+{
+    const int M = 1 << bps;
+    const double sigma = sqrt(noise_var), s2 = sqrt(2.0) * sigma;
+    std::vector<double> FYt(M + 1), delta(M);
+    FYt[0] = 0; FYt[M] = 1;
+    for (int i = 1; i < M; ++i) FYt[i] = mixture_cdf(a, p, M, s2, thr[i]);
+    for (int i = 0; i < M; ++i) delta[i] = FYt[i + 1] - FYt[i];
+    for (int64_t j = 0; j < n; ++j) {
+        const int32_t i = hard_decide(thr, M, y[j]);
+        idx[j] = i;
+        const double F = mixture_cdf(a, p, M, s2, y[j]);
+        n_hat[j] = sign[i] ? (FYt[i + 1] - F) / delta[i] : (F - FYt[i]) / delta[i];
+        for (int k = 0; k < bps; ++k) bits[j * bps + k] = gray_bit(i, k);
+    }
+}
+
+void emu_direct(int bps, const double *a, double two_variance, const double *y, int64_t n, double *llr)
+{
+    for (int64_t j = 0; j < n; ++j) direct_llr(a, 1 << bps, bps, two_variance, y[j], llr + j * bps);
+}
+
+}  // extern "C"
