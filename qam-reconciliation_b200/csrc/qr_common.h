@@ -48,6 +48,7 @@ struct qr_graph {
     int64_t N = 0, C = 0, E = 0;
     int device = -1;
     int32_t max_cdeg = 0, max_vdeg = 0;
+    int32_t var_deg = 0;  // > 0 when every variable node has this degree
     std::vector<int32_t> chk_order;  // [C]   internal check slot -> original check id
     std::vector<int32_t> chk_ptr;    // [C+1] internal check slot -> first CSR slot
     std::vector<int32_t> slot_edge;  // [E]   CSR slot -> original edge id

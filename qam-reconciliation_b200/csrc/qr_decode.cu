@@ -30,17 +30,6 @@ struct Tiling {
     int32_t nxt;      // lane tiles = (lanes / VEC) / bx
 };
 
-template <typename T, int VEC, int D>
-__device__ __forceinline__ uint32_t run_bin(const DecodeParams<T> &P, const LaneInfo<VEC> &L,
-                                            const CheckBin &bin, int32_t first, int32_t stride)
-{
-    uint32_t bad = 0;
-    for (int32_t k = first; k < bin.count; k += stride)
-        bad |= check_item<T, VEC, D>(P, L, bin.chk_begin + k, bin.slot_begin + k * bin.degree,
-                                     bin.degree);
-    return bad;
-}
-
 // DSEL > 0: the graph is check-regular with that degree (only that code path is compiled in, so the
 // register allocation is the one of the hot case); DSEL == 0: any mix of degrees.
 template <typename T, int VEC, int DSEL>
@@ -61,17 +50,17 @@ __device__ __forceinline__ void check_phase(const DecodeParams<T> &P, int cur, c
             for (int32_t b = 0; b < P.n_bins; ++b) {
                 const CheckBin bin = P.bins[b];
                 if (DSEL > 0) {
-                    bad |= run_bin<T, VEC, DSEL>(P, L, bin, first, stride);
+                    bad |= run_check_bin<T, VEC, DSEL>(P, L, bin, first, stride);
                 } else {
                     switch (bin.degree) {
-                    case 2: bad |= run_bin<T, VEC, 2>(P, L, bin, first, stride); break;
-                    case 3: bad |= run_bin<T, VEC, 3>(P, L, bin, first, stride); break;
-                    case 4: bad |= run_bin<T, VEC, 4>(P, L, bin, first, stride); break;
-                    case 5: bad |= run_bin<T, VEC, 5>(P, L, bin, first, stride); break;
-                    case 6: bad |= run_bin<T, VEC, 6>(P, L, bin, first, stride); break;
-                    case 7: bad |= run_bin<T, VEC, 7>(P, L, bin, first, stride); break;
-                    case 8: bad |= run_bin<T, VEC, 8>(P, L, bin, first, stride); break;
-                    default: bad |= run_bin<T, VEC, 0>(P, L, bin, first, stride); break;
+                    case 2: bad |= run_check_bin<T, VEC, 2>(P, L, bin, first, stride); break;
+                    case 3: bad |= run_check_bin<T, VEC, 3>(P, L, bin, first, stride); break;
+                    case 4: bad |= run_check_bin<T, VEC, 4>(P, L, bin, first, stride); break;
+                    case 5: bad |= run_check_bin<T, VEC, 5>(P, L, bin, first, stride); break;
+                    case 6: bad |= run_check_bin<T, VEC, 6>(P, L, bin, first, stride); break;
+                    case 7: bad |= run_check_bin<T, VEC, 7>(P, L, bin, first, stride); break;
+                    case 8: bad |= run_check_bin<T, VEC, 8>(P, L, bin, first, stride); break;
+                    default: bad |= run_check_bin<T, VEC, 0>(P, L, bin, first, stride); break;
                     }
                 }
             }
@@ -104,31 +93,34 @@ __device__ __forceinline__ void var_phase(const DecodeParams<T> &P, int cur, con
         const int32_t jv = xt * tl.bx + tx;
         LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
         decide_lanes<T, VEC>(P, cur, L);
-        if (L.upd | L.fin_ok | L.fin_fail) {
-            for (int32_t n = byid * tl.by + ty; n < P.N; n += gy * tl.by) var_item<T, VEC>(P, L, n);
-        }
+        run_var_range<T, VEC>(P, L, byid * tl.by + ty, gy * tl.by);
         if (byid == 0 && ty == 0) bookkeep_lanes<T, VEC>(P, cur, L);
     }
 }
 
 template <typename T, int VEC, int DSEL>
-__global__ void __launch_bounds__(kBlock) k_check(DecodeParams<T> P, int step, Tiling tl)
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? 2 : 1) k_check(DecodeParams<T> P, int step, Tiling tl)
 {
     __shared__ int32_t s_flags[32 * VEC];
-    if (*(volatile int32_t *)&P.ctrl[CTRL_REMAINING] == 0) return;
+    // Nothing changes CTRL_REMAINING while a check kernel runs, so every CTA sees the same value; the
+    // variable kernel of this step must NOT read it (its own bookkeeping threads decrement it while
+    // later CTAs are still starting), it reads the snapshot taken here instead.
+    const int32_t remaining = *(volatile int32_t *)&P.ctrl[CTRL_REMAINING];
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.ctrl[CTRL_SNAPSHOT] = remaining;
+    if (remaining == 0) return;
     check_phase<T, VEC, DSEL>(P, step & 1, tl, s_flags);
 }
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kBlock) k_var(DecodeParams<T> P, int step, Tiling tl)
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? 2 : 1) k_var(DecodeParams<T> P, int step, Tiling tl)
 {
-    if (*(volatile int32_t *)&P.ctrl[CTRL_REMAINING] == 0) return;
+    if (*(volatile int32_t *)&P.ctrl[CTRL_SNAPSHOT] == 0) return;
     var_phase<T, VEC>(P, step & 1, tl);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[1], 1ULL);
 }
 
 template <typename T, int VEC, int DSEL>
-__global__ void __launch_bounds__(kBlock) k_persistent(DecodeParams<T> P, Tiling tl)
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? 2 : 1) k_persistent(DecodeParams<T> P, Tiling tl)
 {
     __shared__ int32_t s_flags[32 * VEC];
     cg::grid_group grid = cg::this_grid();
@@ -192,13 +184,15 @@ static DecodeParams<T> make_params(const qr_decoder *d, const void *llr, int llr
     P.var_ptr = g->d_var_ptr;
     P.var_slot = g->d_var_slot;
     P.N = g->N; P.C = g->C; P.E = g->E;
-    P.lanes = d->lanes;
+    P.var_deg = g->var_deg;
+    // a batch smaller than the workspace uses a narrower layout, so no CTA is left with idle lanes only
+    P.lanes = (int32_t)std::min<int64_t>(d->lanes, (frames + 31) / 32 * 32);
     P.c2v = static_cast<T *>(d->c2v);
     P.post = static_cast<T *>(d->post);
     P.llr = static_cast<T *>(d->llr);
     P.synd = d->synd;
-    P.st[0] = d->st; P.st[1] = d->st + d->lanes;
-    P.unsat[0] = d->unsat; P.unsat[1] = d->unsat + d->lanes;
+    P.st[0] = d->st; P.st[1] = d->st + P.lanes;
+    P.unsat[0] = d->unsat; P.unsat[1] = d->unsat + P.lanes;
     P.llr_in = llr; P.llr_in_f64 = llr_dtype == QR_F64;
     P.synd_in = synd;
     P.frames = frames; P.maxiter = maxiter;
@@ -230,7 +224,7 @@ template <typename T, int DSEL>
 static int run_batch_t(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream)
 {
     constexpr int VEC = Prec<T>::VEC;
-    const Tiling tl = make_tiling<VEC>(d->lanes);
+    const Tiling tl = make_tiling<VEC>(P.lanes);
     if (d->schedule == QR_SCHED_PERSISTENT) {
         int per_sm = 0;
         QR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<T, VEC, DSEL>,
@@ -247,10 +241,11 @@ static int run_batch_t(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t str
     }
     // launch-per-phase schedule: the host looks at the remaining-frames word every few steps
     const int grid = grid_for(4 * d->sm_count, tl.nxt);
-    const int64_t rounds = (P.frames + d->lanes - 1) / d->lanes;
+    const int64_t rounds = (P.frames + P.lanes - 1) / P.lanes;
     const int64_t max_steps = rounds * ((int64_t)P.maxiter + 2) + 2;
+    const int chunk = P.maxiter + 1;   // a lane finishes a frame at least every maxiter + 1 steps
     for (int64_t step = 0; step < max_steps;) {
-        for (int k = 0; k < 8 && step < max_steps; ++k, ++step) {
+        for (int k = 0; k < chunk && step < max_steps; ++k, ++step) {
             k_check<T, VEC, DSEL><<<grid, kBlock, 0, stream>>>(P, (int)(step & 1), tl);
             k_var<T, VEC><<<grid, kBlock, 0, stream>>>(P, (int)(step & 1), tl);
         }
@@ -299,10 +294,13 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
         const size_t w = precision == QR_F64 ? 8 : 4;
         const size_t per_lane = (size_t)g->E * w + 2 * (size_t)g->N * w + (size_t)g->C;
         if (lanes == 0) {
-            // default: keep the resident frames' messages inside L2 (about 3/4 of it)
-            size_t budget = (size_t)prop.l2CacheSize / 4 * 3;
-            lanes = (int64_t)(budget / per_lane) / 32 * 32;
-            lanes = std::min<int64_t>(std::max<int64_t>(lanes, 32), 1024);
+            // default: 512 frames in flight (measured optimum of the HBM-streaming regime on B200:
+            // enough rows per phase to hide launch/barrier cost, workspace still small), less if
+            // device memory is short
+            size_t free_b = 0, total_b = 0;
+            QR_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+            lanes = 512;
+            while (lanes > 32 && (size_t)lanes * per_lane > free_b / 4) lanes /= 2;
         }
         lanes = (lanes + 31) / 32 * 32;
         d->lanes = (int32_t)lanes;
@@ -374,8 +372,9 @@ int qr_decode_batch(qr_decoder *d, const void *d_llr, int llr_dtype, const uint8
     cudaGetDevice(&prev);
     auto body = [&]() -> int {
         QR_CUDA_CHECK(cudaSetDevice(d->device));
-        qr::k_init_batch<<<(d->lanes + 255) / 256, 256, 0, stream>>>(
-            d->st, d->st + d->lanes, d->unsat, d->unsat + d->lanes, d->lanes, frames, d->ctrl, d->stats);
+        const int32_t lanes = (int32_t)std::min<int64_t>(d->lanes, (frames + 31) / 32 * 32);
+        qr::k_init_batch<<<(lanes + 255) / 256, 256, 0, stream>>>(
+            d->st, d->st + lanes, d->unsat, d->unsat + lanes, lanes, frames, d->ctrl, d->stats);
         QR_CUDA_CHECK(cudaGetLastError());
         d->last_stream = stream;
         if (d->precision == QR_F64) {

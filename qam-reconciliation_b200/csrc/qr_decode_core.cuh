@@ -45,7 +45,7 @@ struct LaneState {
     int32_t pad;
 };
 
-enum : int { CTRL_NEXT_FRAME = 0, CTRL_REMAINING = 1, CTRL_WORDS = 8 };
+enum : int { CTRL_NEXT_FRAME = 0, CTRL_REMAINING = 1, CTRL_SNAPSHOT = 2, CTRL_WORDS = 8 };
 
 template <typename T>
 struct DecodeParams {
@@ -54,6 +54,7 @@ struct DecodeParams {
     int32_t n_bins;
     const int32_t *chk_order, *slot_var, *var_ptr, *var_slot;
     int64_t N, C, E;
+    int32_t var_deg;  // > 0: every variable has this degree (var_slot row of n starts at n * var_deg)
     // workspace
     int32_t lanes;
     T *c2v, *post, *llr;
@@ -515,6 +516,154 @@ QR_HD void bookkeep_lanes(const DecodeParams<T> &P, int cur, const LaneInfo<VEC>
         P.st[nxt][lane] = s;
         P.unsat[nxt][lane] = 0;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FAST PATHS.  The per-item functions above are general (fresh lanes, run-time degrees); the hot
+// loops below cover the steady state -- no fresh lane in the thread's vector, compile-time check
+// degree, regular variable degree -- and are written for memory-level parallelism: the index row of
+// the NEXT item is fetched while the current one computes, and all 2*D (check) or DV+1 (variable)
+// 128-bit row loads of an item are issued back to back before anything consumes them.
+
+template <int D>
+QR_HD void load_index_row(const int32_t *__restrict__ tab, int32_t first, int32_t (&v)[D])
+{
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = tab[first + i];
+}
+
+template <typename T, int VEC, int D>
+QR_HD uint32_t check_item_fast(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t ci, int32_t slot0,
+                               const int32_t (&v)[D])
+{
+    const int32_t lanes = P.lanes;
+    Vec<T, VEC> pv[D], x[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) pv[i] = ld_row<T, VEC>(P.post, v[i], lanes, L.l0);
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = ld_row<T, VEC>(P.c2v, slot0 + i, lanes, L.l0);
+    const Vec<uint8_t, VEC> sy = *reinterpret_cast<const Vec<uint8_t, VEC> *>(P.synd + (int64_t)ci * lanes + L.l0);
+    uint32_t par = 0;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) par |= (uint32_t)(sy.v[k] & 1u) << k;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            par ^= (uint32_t)(pv[i].v[k] < (T)0) << k;       // decoder.pyx:244 (strict <)
+            x[i].v[k] = pv[i].v[k] - x[i].v[k];               // decoder.pyx:295-297
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        T xs[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) xs[i] = x[i].v[k];
+        MathOf<T>::template run<D, D>(D, xs, (sy.v[k] & 1u) != 0);
+#pragma unroll
+        for (int i = 0; i < D; ++i) x[i].v[k] = xs[i];
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) st_row<T, VEC>(P.c2v, slot0 + i, lanes, L.l0, x[i]);
+    return par & L.active;
+}
+
+// All checks k = first, first+stride, ... of one degree bin, for the thread's lanes.
+template <typename T, int VEC, int D>
+QR_HD uint32_t run_check_bin(const DecodeParams<T> &P, const LaneInfo<VEC> &L, const CheckBin &bin,
+                             int32_t first, int32_t stride)
+{
+    uint32_t bad = 0;
+    if constexpr (D > 0) {
+        if (!L.fresh) {
+            int32_t cur[D], nxt[D];
+            if (first < bin.count) load_index_row<D>(P.slot_var, bin.slot_begin + first * D, cur);
+            for (int32_t k = first; k < bin.count; k += stride) {
+                const int32_t kn = k + stride;
+                if (kn < bin.count) load_index_row<D>(P.slot_var, bin.slot_begin + kn * D, nxt);
+                bad |= check_item_fast<T, VEC, D>(P, L, bin.chk_begin + k, bin.slot_begin + k * D, cur);
+#pragma unroll
+                for (int i = 0; i < D; ++i) cur[i] = nxt[i];
+            }
+            return bad;
+        }
+    }
+    for (int32_t k = first; k < bin.count; k += stride)
+        bad |= check_item<T, VEC, D>(P, L, bin.chk_begin + k, bin.slot_begin + k * bin.degree, bin.degree);
+    return bad;
+}
+
+template <typename T, int VEC, int DV>
+QR_HD void var_item_fast(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t n, const int32_t (&slot)[DV])
+{
+    const int32_t lanes = P.lanes;
+    Vec<T, VEC> acc = ld_row<T, VEC>(P.llr, n, lanes, L.l0);
+    Vec<T, VEC> m[DV];
+#pragma unroll
+    for (int i = 0; i < DV; ++i) m[i] = ld_row<T, VEC>(P.c2v, slot[i], lanes, L.l0);
+#pragma unroll
+    for (int i = 0; i < DV; ++i) {                        // ascending edge id: decoder.pyx:291-293
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc.v[k] = acc.v[k] + m[i].v[k];
+    }
+    st_row<T, VEC>(P.post, n, lanes, L.l0, acc);
+}
+
+template <typename T, int VEC, int DV, int U>
+QR_HD void run_var_fast(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t first, int32_t stride)
+{
+    // U variables per trip (n, n+stride, ...): U*(DV+1) independent row loads in flight per thread;
+    // the slot rows of the next trip are fetched while this one is summed.
+    const int32_t N = (int32_t)P.N, lanes = P.lanes;
+    int32_t cur[U][DV], nxt[U][DV];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (first + u * stride < N) load_index_row<DV>(P.var_slot, (first + u * stride) * DV, cur[u]);
+    for (int32_t n = first; n < N; n += U * stride) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int32_t nn = n + (U + u) * stride;
+            if (nn < N) load_index_row<DV>(P.var_slot, nn * DV, nxt[u]);
+        }
+        if (n + (U - 1) * stride < N) {
+            Vec<T, VEC> acc[U], m[U][DV];
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc[u] = ld_row<T, VEC>(P.llr, n + u * stride, lanes, L.l0);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int i = 0; i < DV; ++i) m[u][i] = ld_row<T, VEC>(P.c2v, cur[u][i], lanes, L.l0);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int i = 0; i < DV; ++i)                  // ascending edge id: decoder.pyx:291-293
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[u].v[k] = acc[u].v[k] + m[u][i].v[k];
+                st_row<T, VEC>(P.post, n + u * stride, lanes, L.l0, acc[u]);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (n + u * stride < N) var_item_fast<T, VEC, DV>(P, L, n + u * stride, cur[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int i = 0; i < DV; ++i) cur[u][i] = nxt[u][i];
+    }
+}
+
+// All variables n = first, first+stride, ... for the thread's lanes (decisions already in L).
+template <typename T, int VEC>
+QR_HD void run_var_range(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t first, int32_t stride)
+{
+    if (!(L.upd | L.fin_ok | L.fin_fail)) return;
+    const bool steady = !L.fresh && !(L.fin_ok | L.fin_fail) && L.upd == L.active;
+    constexpr int U = 2;  // 4 was measured slower on B200 (register spills in the persistent kernel)
+    if (steady && P.var_deg == 3) { run_var_fast<T, VEC, 3, U>(P, L, first, stride); return; }
+    if (steady && P.var_deg == 4) { run_var_fast<T, VEC, 4, U>(P, L, first, stride); return; }
+    if (steady && P.var_deg == 2) { run_var_fast<T, VEC, 2, U>(P, L, first, stride); return; }
+    for (int32_t n = first; n < P.N; n += stride) var_item<T, VEC>(P, L, n);
 }
 
 }  // namespace qr

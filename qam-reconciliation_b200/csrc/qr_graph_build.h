@@ -27,6 +27,7 @@ inline int build_host_tables(qr_graph &g, const int64_t *vid, const int64_t *cid
     for (int64_t e = 0; e < E; ++e) { cdeg[cid[e]]++; vdeg[vid[e]]++; }
     g.max_cdeg = *std::max_element(cdeg.begin(), cdeg.end());
     g.max_vdeg = *std::max_element(vdeg.begin(), vdeg.end());
+    g.var_deg = (*std::min_element(vdeg.begin(), vdeg.end()) == g.max_vdeg) ? g.max_vdeg : 0;
     for (int64_t c = 0; c < C; ++c) {
         // the reference indexes its 2*(deg-1) scratch out of bounds for degree 1 and dereferences a
         // failed malloc for degree 0 (decoder.pyx:131-135, :337-342): reject instead

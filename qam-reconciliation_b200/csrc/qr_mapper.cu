@@ -119,12 +119,10 @@ __global__ void __launch_bounds__(128) k_demap(MapperView m, const double *__res
         const int32_t j = (int32_t)tx[sidx];
         double N[kMaxBps], D[kMaxBps];
         for (int k = 0; k < m.bps; ++k) { N[k] = 0; D[k] = 0; }
-        double cum = 0;
         for (int i = 0; i < m.order; ++i) {
             const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
-            const double yh = fast ? g_inv_fast(s.a, s.p, m.order, m.sigma, m.s2, target, 1e-9, i, cum)
+            const double yh = fast ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i)
                                    : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
-            cum += s.p[i];
             // the body of demap_from_yhat for one i (kept inline: y_hat need not be stored)
             double sum = 0;
             for (int k = 0; k < j; ++k) {
@@ -164,9 +162,7 @@ __global__ void __launch_bounds__(128) k_g_inv(MapperView m, const double *__res
          j += (int64_t)gridDim.x * blockDim.x) {
         const int32_t i = (int32_t)region[j];
         const double target = inv_target(s.sign, s.FYt, s.delta, n_hat[j], i);
-        double cum = 0;
-        for (int k = 0; k < i; ++k) cum += s.p[k];
-        y_hat[j] = (mode & 1) ? g_inv_fast(s.a, s.p, m.order, m.sigma, m.s2, target, 1e-9, i, cum)
+        y_hat[j] = (mode & 1) ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i)
                               : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
     }
 }

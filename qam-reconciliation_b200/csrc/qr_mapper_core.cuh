@@ -186,48 +186,94 @@ QR_HD double norm_quantile(double q)
            (((((b1 * r + b2) * r + b3) * r + b4) * r + b5) * r + 1);
 }
 
-// Fast variant of g_inv_search.  The bisection's outcome is a function of the root y* alone (F is
-// monotone: F(mid) > target  <=>  mid > y*), so: same bracket as the reference, a safeguarded
-// Newton iteration for y* (a handful of F evaluations instead of ~35), then the reference's
-// halving sequence replayed with comparisons against y* -- no F evaluations -- which lands in the
-// same 1e-9 cell and returns the same midpoint unless y* is within the Newton error of a midpoint.
-QR_HD double g_inv_fast(const double *a, const double *p, int order, double sigma, double s2,
-                        double target, double accuracy, int32_t region, double cum_below)
+// Fast variant of g_inv_search.  The bisection's outcome is a function of the root y* of
+// F_Y(y) = target alone (F_Y is monotone: F(mid) > target  <=>  mid > y*; the doubling loop likewise
+// compares powers of two with y*).  So: bracket y* analytically (interior regions: the decision
+// thresholds, whose F values are the stored F_Y_thresholds; outer regions: single-Gaussian bounds),
+// solve with a safeguarded Halley iteration (2-3 evaluations of F, f, f' instead of ~35 of F), then
+// replay the reference's doubling and halving with comparisons against y* -- no F evaluations --
+// which lands in the same 1e-9 cell and returns the same midpoint unless y* is within the solver
+// error (~1e-14) of a midpoint.  Saturated targets (<= 0 or >= 1), whose result is defined by where
+// erf rounds to +-1, take the exact path.
+QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, const double *FYt, int order,
+                        double sigma, double s2, double target, double accuracy, int32_t region)
 {
-    Bracket b = bracket_root(a, p, order, s2, target);
-    double lo = b.lo, hi = b.hi;
-    double root;
-    // degenerate ends: F never rises above (or falls below) the target inside the bracket
-    const bool upper = target > .5;
-    if (upper && !(b.f_end > target)) {
-        root = hi;               // F(hi) == target (plateau or exact hit): every midpoint goes to lo
-    } else if (!upper && b.f_end > target) {
-        root = lo;               // doubling gave up (cannot happen for target >= 0)
+    if (!(target > 0.0 && target < 1.0)) return g_inv_exact(a, p, order, s2, target, accuracy);
+    double rlo, rhi, y;
+    if (region > 0 && region < order - 1) {
+        rlo = thr[region];
+        rhi = thr[region + 1];
+        const double t0 = FYt[region], t1 = FYt[region + 1];
+        if (!(target >= t0 && target <= t1)) return g_inv_exact(a, p, order, s2, target, accuracy);
+        y = rlo + (target - t0) / (t1 - t0) * (rhi - rlo);
+    } else if (region == 0) {
+        // p_0 Phi((y-a_0)/s) <= F(y) <= Phi((y-a_0)/s)
+        rhi = thr[1];
+        rlo = a[0] + sigma * norm_quantile(target) - 1e-6 * sigma;
+        const double q = target / p[0];
+        if (q < 1.0) rhi = fmin(rhi, a[0] + sigma * norm_quantile(q) + 1e-6 * sigma);
+        if (!(FYt[1] >= target)) return g_inv_exact(a, p, order, s2, target, accuracy);
+        y = rhi;
     } else {
-        // invariant: F(rlo) <= target < F(rhi)
-        double rlo = lo, rhi = hi;
-        if (!upper && mixture_cdf(a, p, order, s2, hi) <= target) {
-            root = hi;           // F(0) <= target <= .5: the reference walks up to hi as well
-        } else {
-            // start from the quantile of the region's own Gaussian
-            double q = (target - cum_below) / p[region];
-            q = q < 1e-300 ? 1e-300 : (q > 1 - 1e-16 ? 1 - 1e-16 : q);
-            double y = a[region] + sigma * norm_quantile(q);
-            if (!(y > rlo && y < rhi)) y = 0.5 * (rlo + rhi);
-            root = y;
-            for (int it = 0; it < 200; ++it) {
-                const double F = mixture_cdf(a, p, order, s2, y);
-                if (F > target) rhi = y; else rlo = y;
-                const double f = mixture_pdf(a, p, order, sigma, y);
-                double yn = y - (F - target) / f;
-                if (!(yn > rlo && yn < rhi)) yn = 0.5 * (rlo + rhi);   // Newton left the bracket
-                const double step = fabs(yn - y);
-                y = yn;
-                root = y;
-                if (step <= 4e-16 * fmax(1.0, fabs(y)) || (rhi - rlo) <= 1e-15 * fmax(1.0, fabs(y))) break;
-            }
-            // settle on the side the comparisons imply: root = sup{ y : F(y) <= target }
+        // Phi((y-a_top)/s) <= F(y) <= 1 - p_top + p_top Phi((y-a_top)/s)
+        const int top = order - 1;
+        rlo = thr[top];
+        rhi = a[top] + sigma * norm_quantile(target) + 1e-6 * sigma;
+        const double q = (target - (1.0 - p[top])) / p[top];
+        if (q > 0.0) rlo = fmax(rlo, a[top] + sigma * norm_quantile(q) - 1e-6 * sigma);
+        if (!(FYt[top] <= target)) return g_inv_exact(a, p, order, s2, target, accuracy);
+        y = rlo;
+    }
+    if (!(rlo < rhi)) return g_inv_exact(a, p, order, s2, target, accuracy);
+    if (!(y > rlo && y < rhi)) y = 0.5 * (rlo + rhi);
+    const double c0 = 0.3989422804014327 / sigma, c1 = c0 / (sigma * sigma);
+    double root = y;
+    double f = 1;
+    // n_hat exactly 0 or 1 puts the target exactly on a stored threshold value: the root is the
+    // decision threshold itself (a dyadic point for the usual constellations, where "mid > root"
+    // must be decided exactly as the reference's "F(mid) > target" is)
+    const bool at_lo = region > 0 && target == FYt[region];
+    const bool at_hi = region < order - 1 && target == FYt[region + 1];
+    if (at_lo) root = thr[region];
+    if (at_hi) root = thr[region + 1];
+    for (int it = 0; it < 100 && !(at_lo || at_hi); ++it) {
+        double F = 0, fp = 0;
+        f = 0;
+        for (int k = 0; k < order; ++k) {
+            const double d = y - a[k];
+            const double z = d / s2;
+            const double e = p[k] * exp(-z * z);
+            F += p[k] * (0.5 * (1 + erf(z)));
+            f += e;
+            fp -= e * d;
         }
+        f *= c0;
+        fp *= c1;
+        const double g = F - target;
+        if (g > 0) rhi = y; else rlo = y;
+        const double den = 2 * f * f - g * fp;
+        bool cubic = den > 0 && f > 0;
+        double step = cubic ? 2 * g * f / den : g / f;
+        double yn = y - step;
+        bool safe = yn > rlo && yn < rhi;
+        if (!safe) { yn = 0.5 * (rlo + rhi); step = y - yn; }
+        y = yn;
+        root = y;
+        // Halley: the next error is ~ step^3 / sigma^2, Newton: ~ step^2 / sigma
+        if (safe && fabs(step) <= (cubic ? 1e-5 : 3e-8) * sigma) break;
+        if ((rhi - rlo) <= 4e-16 * fmax(1.0, fabs(y))) break;
+    }
+    // Deep in the tails F is flat at the resolution of a double (one ulp of F spans f^-1 * 1e-16 in y):
+    // there the reference's answer is set by the rounding of F, not by the root.  Replay it exactly.
+    if (!(f * accuracy > 1e-14)) return g_inv_exact(a, p, order, s2, target, accuracy);
+    // replay of noisemapper.pyx:319-344 against the root
+    double lo, hi;
+    if (target > .5) {
+        hi = 1; lo = 0;
+        for (int it = 0; hi < root && it < kMaxDoublings; ++it) { lo = hi; hi *= 2.; }
+    } else {
+        lo = -1; hi = 0;
+        for (int it = 0; lo > root && it < kMaxDoublings; ++it) { hi = lo; lo *= 2.; }
     }
     for (int it = 0; (hi - lo) > accuracy && it < kMaxHalvings; ++it) {
         const double mid = (hi + lo) / 2;

@@ -26,9 +26,9 @@ using namespace qr;
 template <typename T, int VEC, int D>
 static uint32_t emu_bin(const DecodeParams<T> &P, const LaneInfo<VEC> &L, const CheckBin &bin)
 {
+    // split the bin over a few emulated "threads" so the prefetch pipeline sees first/stride > trivial
     uint32_t bad = 0;
-    for (int32_t k = 0; k < bin.count; ++k)
-        bad |= check_item<T, VEC, D>(P, L, bin.chk_begin + k, bin.slot_begin + k * bin.degree, bin.degree);
+    for (int32_t t = 0; t < 3; ++t) bad |= run_check_bin<T, VEC, D>(P, L, bin, t, 3);
     return bad;
 }
 
@@ -50,7 +50,7 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
     P.bins = g.bins.data(); P.n_bins = (int32_t)g.bins.size();
     P.chk_order = g.chk_order.data(); P.slot_var = g.slot_var.data();
     P.var_ptr = g.var_ptr.data(); P.var_slot = g.var_slot.data();
-    P.N = g.N; P.C = g.C; P.E = g.E; P.lanes = lanes;
+    P.N = g.N; P.C = g.C; P.E = g.E; P.lanes = lanes; P.var_deg = g.var_deg;
     P.c2v = c2v.data(); P.post = postw.data(); P.llr = llrw.data(); P.synd = syndw.data();
     P.st[0] = st.data(); P.st[1] = st.data() + lanes;
     P.unsat[0] = unsat.data(); P.unsat[1] = unsat.data() + lanes;
@@ -93,8 +93,7 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
         for (int jv = 0; jv < LV; ++jv) {
             LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
             decide_lanes<T, VEC>(P, cur, L);
-            if (L.upd | L.fin_ok | L.fin_fail)
-                for (int32_t n = 0; n < g.N; ++n) var_item<T, VEC>(P, L, n);
+            for (int32_t t = 0; t < 5; ++t) run_var_range<T, VEC>(P, L, t, 5);
             bookkeep_lanes<T, VEC>(P, cur, L);
         }
     }
@@ -149,12 +148,10 @@ void emu_demap(int bps, const double *a, const double *thr, const double *p, dou
     for (int i = 0; i < M; ++i) delta[i] = FYt[i + 1] - FYt[i];
     std::vector<double> yh(M);
     for (int64_t s = 0; s < n; ++s) {
-        double cum = 0;
         for (int i = 0; i < M; ++i) {
             const double target = inv_target(sign, FYt.data(), delta.data(), n_hat[s], i);
-            yh[i] = (mode & 1) ? g_inv_fast(a, p, M, sigma, s2, target, 1e-9, i, cum)
+            yh[i] = (mode & 1) ? g_inv_fast(a, p, thr, FYt.data(), M, sigma, s2, target, 1e-9, i)
                                : g_inv_exact(a, p, M, s2, target, 1e-9);
-            cum += p[i];
             if (yhat_out) yhat_out[s * M + i] = yh[i];
         }
         demap_from_yhat(a, p, delta.data(), M, bps, 2 * noise_var, yh.data(), (int32_t)tx[s], (mode & 2) != 0,

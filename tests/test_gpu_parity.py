@@ -159,11 +159,13 @@ def test_mapper_fixture(qr, path):
     # tables: device erf vs scipy/libm erf
     np.testing.assert_allclose(nm.F_Y_thresholds, g["F_Y_thresholds"], rtol=0, atol=4e-16)
     np.testing.assert_allclose(nm.delta_F_Y, g["delta_F_Y"], rtol=0, atol=8e-16)
-    np.testing.assert_allclose(nm.fwrd_transition_probability, g["fwrd"], rtol=1e-12, atol=1e-300)
-    np.testing.assert_allclose(nm.back_transition_probability, g["back"], rtol=1e-12, atol=1e-300)
+    # differences of two erf values near +-1: absolute error of a few ulp of 1, whatever the entry's size
+    np.testing.assert_allclose(nm.fwrd_transition_probability, g["fwrd"], rtol=1e-12, atol=3e-16)
+    np.testing.assert_allclose(nm.back_transition_probability, g["back"], rtol=1e-12, atol=3e-16)
     np.testing.assert_allclose(nm.inf_erf_table, g["inf_erf_table"], rtol=0, atol=4e-16)
     fin = np.isfinite(g["bare_llr_table"]) & (np.abs(g["bare_llr_table"]) < 1e299)
-    np.testing.assert_allclose(nm.bare_llr_table[fin], g["bare_llr_table"][fin], rtol=1e-10, atol=1e-10)
+    # log of ratios of those entries: tail entries of ~1e-8 carry ~1e-8 relative error
+    np.testing.assert_allclose(nm.bare_llr_table[fin], g["bare_llr_table"][fin], rtol=1e-9, atol=1e-7)
     assert np.array_equal(nm.bare_llr_table[~fin], g["bare_llr_table"][~fin])
     # integers: bit exact
     idx = nm.hard_decide_index(g["y"])
@@ -173,17 +175,29 @@ def test_mapper_fixture(qr, path):
     # softening metric: |n - n_ref| <= 1e-14 (ratio of two erf sums)
     np.testing.assert_allclose(nm.map_noise(g["y"], idx), g["n_hat"], rtol=0, atol=1e-14)
     # LLRs, exact-bisection mode: 1e-9 relative (+1e-9 absolute near 0)
+    # n within 1e-9 of 0 or 1 puts some reconstructed samples > 6 sigma into a tail, where F_Y is flat
+    # at the resolution of a double (n exactly 0 or 1: F_Y saturated).  There the bisection converges
+    # to wherever erf's ROUNDING flips the comparison -- a property of the erf implementation (CUDA's
+    # and libm's differ by up to ~3e-3 in y) -- so those entries only get a 2 % tolerance.  Such
+    # samples have probability < 1e-8 per symbol.
     for nk, jk, lk in (("n_hat", "x", "lappr"), ("n_grid", "j_grid", "lappr_grid")):
-        np.testing.assert_allclose(nm.demap_lappr_array(g[nk], g[jk]), g[lk], rtol=1e-9, atol=1e-9)
+        sat = np.repeat((g[nk] < 1e-9) | (g[nk] > 1 - 1e-9), bps)
+        got = nm.demap_lappr_array(g[nk], g[jk])
+        np.testing.assert_allclose(got[~sat], g[lk][~sat], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(got[sat], g[lk][sat], rtol=2e-2, atol=1e-9)
         fast = nm.demap_lappr_array_batch(g[nk], g[jk], mode="fast").cpu().numpy()
-        np.testing.assert_allclose(fast, g[lk], rtol=1e-7, atol=1e-7)
+        np.testing.assert_allclose(fast[~sat], g[lk][~sat], rtol=1e-7, atol=1e-7)
+        np.testing.assert_allclose(fast[sat], g[lk][sat], rtol=2e-2, atol=1e-9)
     M = pa.order
     yh = nm.g_inv_search_batch(np.repeat(g["n_grid"][:8], M), np.tile(np.arange(M), 8)).cpu().numpy().reshape(8, M)
-    np.testing.assert_allclose(yh, g["yhat_grid"], rtol=0, atol=2e-9)
+    inner = (g["n_grid"][:8] > 1e-9) & (g["n_grid"][:8] < 1 - 1e-9)
+    np.testing.assert_allclose(yh[inner], g["yhat_grid"][inner], rtol=0, atol=2e-9)
+    np.testing.assert_allclose(yh[~inner], g["yhat_grid"][~inner], rtol=0, atol=0.2)   # erf rounding boundary
     assert nm.g_inv_search(float(g["n_grid"][3]), 0) == pytest.approx(g["yhat_grid"][3, 0], abs=2e-9)
     bare = nm.bare_llr(g["x"])
     fin = np.abs(g["bare"]) < 1e299
-    np.testing.assert_allclose(bare[fin], g["bare"][fin], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(bare[fin], g["bare"][fin], rtol=1e-9, atol=1e-7)
+    assert np.array_equal(bare[~fin], g["bare"][~fin])
     np.testing.assert_allclose(nm.direct_llr_batch(g["y"]).cpu().numpy(), g["direct"], rtol=1e-12, atol=1e-12,
                                equal_nan=True)
     with pytest.raises(ValueError):
@@ -288,7 +302,8 @@ def test_fp32_batch_tracks_oracle(qr, orc):
         assert (ok == ook).mean() >= 0.97
         both = (ok == 1) & (ook == 1)
         assert np.abs(it[both] - oit[both]).max() <= 2
-        assert np.array_equal(post[both] < 0, opost[both] < 0)          # same decoded words
+        ndiff = ((post[both] < 0) != (opost[both] < 0)).sum(axis=1)
+        assert ndiff.sum() == 0, (schedule, np.flatnonzero(ndiff), ndiff[ndiff > 0], it[both][ndiff > 0], oit[both][ndiff > 0])
         assert np.array_equal((post[both] < 0).astype(np.uint8), word[both])
         # converged frames satisfy their syndrome (checked on the device) and re-decode in 0 iterations
         assert dec.check_lappr_batch(post[both], synd[both]).cpu().numpy().all()
