@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 
 #include "qr_decode_core.cuh"
@@ -24,6 +25,13 @@ namespace cg = cooperative_groups;
 namespace qr {
 
 constexpr int kBlock = 256;
+
+// resident CTAs per SM the kernels are compiled for (caps registers per thread at 65536 / (256 * n))
+template <typename T, int VEC>
+constexpr int min_ctas()
+{
+    return sizeof(T) == 8 ? 1 : (VEC >= 4 ? 2 : (VEC == 2 ? 3 : 4));
+}
 
 struct Tiling {
     int32_t bx, by;   // CTA tile
@@ -93,13 +101,100 @@ __device__ __forceinline__ void var_phase(const DecodeParams<T> &P, int cur, con
         const int32_t jv = xt * tl.bx + tx;
         LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
         decide_lanes<T, VEC>(P, cur, L);
-        run_var_range<T, VEC>(P, L, byid * tl.by + ty, gy * tl.by);
+        run_var_range<T, VEC>(P, L, byid * tl.by + ty, gy * tl.by, (int32_t)P.N);
+        if (byid == 0 && ty == 0) bookkeep_lanes<T, VEC>(P, cur, L);
+    }
+}
+
+// ---- work-stealing variants for the persistent kernel: rows are claimed in chunks of by*kRowsPerClaim from
+// a per-lane-tile counter, so a slow SM (far L2 die, unlucky DRAM pages) does not hold the grid barrier.
+constexpr int kRowsPerClaim = 8;
+
+template <typename T, int VEC, int DSEL>
+__device__ __forceinline__ void check_phase_dyn(const DecodeParams<T> &P, int cur, const Tiling tl,
+                                                int32_t *s_flags, int32_t *s_base)
+{
+    const int32_t tx = threadIdx.x % tl.bx, ty = threadIdx.x / tl.bx;
+    const int32_t G = gridDim.x;
+    const int32_t gx = min(tl.nxt, G);
+    const int32_t bxid = blockIdx.x % gx, byid = blockIdx.x / gx;
+    const int32_t claim = tl.by * kRowsPerClaim, C = (int32_t)P.C;
+    for (int32_t xt = bxid; xt < tl.nxt; xt += gx) {
+        const int32_t jv = xt * tl.bx + tx;
+        const LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
+        if (byid == 0 && threadIdx.x == 0) P.work[kMaxLaneTiles + xt] = 0;   // variable-phase counter of this step
+        uint32_t bad = 0;
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) *s_base = atomicAdd(&P.work[xt], claim);
+            __syncthreads();
+            const int32_t c0 = *s_base;
+            if (c0 >= C) break;
+            const int32_t c1 = min(c0 + claim, C);
+            if (!L.active) continue;
+            for (int32_t b = 0; b < P.n_bins; ++b) {
+                const CheckBin bin = P.bins[b];
+                const int32_t lo = max(c0, bin.chk_begin), hi = min(c1, bin.chk_begin + bin.count);
+                if (lo >= hi) continue;
+                const CheckBin sub{bin.degree, lo, hi - lo, bin.slot_begin + (lo - bin.chk_begin) * bin.degree};
+                if (DSEL > 0) {
+                    bad |= run_check_bin<T, VEC, DSEL>(P, L, sub, ty, tl.by);
+                } else {
+                    switch (bin.degree) {
+                    case 2: bad |= run_check_bin<T, VEC, 2>(P, L, sub, ty, tl.by); break;
+                    case 3: bad |= run_check_bin<T, VEC, 3>(P, L, sub, ty, tl.by); break;
+                    case 4: bad |= run_check_bin<T, VEC, 4>(P, L, sub, ty, tl.by); break;
+                    case 5: bad |= run_check_bin<T, VEC, 5>(P, L, sub, ty, tl.by); break;
+                    case 6: bad |= run_check_bin<T, VEC, 6>(P, L, sub, ty, tl.by); break;
+                    case 7: bad |= run_check_bin<T, VEC, 7>(P, L, sub, ty, tl.by); break;
+                    case 8: bad |= run_check_bin<T, VEC, 8>(P, L, sub, ty, tl.by); break;
+                    default: bad |= run_check_bin<T, VEC, 0>(P, L, sub, ty, tl.by); break;
+                    }
+                }
+            }
+        }
+        for (int32_t i = threadIdx.x; i < tl.bx * VEC; i += blockDim.x) s_flags[i] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+            if (bad >> k & 1) s_flags[tx * VEC + k] = 1;
+        __syncthreads();
+        if (ty == 0) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                if (s_flags[tx * VEC + k]) P.unsat[cur][L.l0 + k] = 1;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void var_phase_dyn(const DecodeParams<T> &P, int cur, const Tiling tl, int32_t *s_base)
+{
+    const int32_t tx = threadIdx.x % tl.bx, ty = threadIdx.x / tl.bx;
+    const int32_t G = gridDim.x;
+    const int32_t gx = min(tl.nxt, G);
+    const int32_t bxid = blockIdx.x % gx, byid = blockIdx.x / gx;
+    const int32_t claim = tl.by * kRowsPerClaim, N = (int32_t)P.N;
+    for (int32_t xt = bxid; xt < tl.nxt; xt += gx) {
+        const int32_t jv = xt * tl.bx + tx;
+        LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
+        decide_lanes<T, VEC>(P, cur, L);
+        if (byid == 0 && threadIdx.x == 0) P.work[xt] = 0;                    // check-phase counter of the next step
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) *s_base = atomicAdd(&P.work[kMaxLaneTiles + xt], claim);
+            __syncthreads();
+            const int32_t n0 = *s_base;
+            if (n0 >= N) break;
+            run_var_range<T, VEC>(P, L, n0 + ty, tl.by, min(n0 + claim, N));
+        }
         if (byid == 0 && ty == 0) bookkeep_lanes<T, VEC>(P, cur, L);
     }
 }
 
 template <typename T, int VEC, int DSEL>
-__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? 2 : 1) k_check(DecodeParams<T> P, int step, Tiling tl)
+__global__ void __launch_bounds__(kBlock, min_ctas<T, VEC>()) k_check(DecodeParams<T> P, int step, Tiling tl)
 {
     __shared__ int32_t s_flags[32 * VEC];
     // Nothing changes CTRL_REMAINING while a check kernel runs, so every CTA sees the same value; the
@@ -112,7 +207,7 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? 2 : 1) k_check(Decode
 }
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? 2 : 1) k_var(DecodeParams<T> P, int step, Tiling tl)
+__global__ void __launch_bounds__(kBlock, min_ctas<T, VEC>()) k_var(DecodeParams<T> P, int step, Tiling tl)
 {
     if (*(volatile int32_t *)&P.ctrl[CTRL_SNAPSHOT] == 0) return;
     var_phase<T, VEC>(P, step & 1, tl);
@@ -120,14 +215,15 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? 2 : 1) k_var(DecodePa
 }
 
 template <typename T, int VEC, int DSEL>
-__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? 2 : 1) k_persistent(DecodeParams<T> P, Tiling tl)
+__global__ void __launch_bounds__(kBlock, min_ctas<T, VEC>()) k_persistent(DecodeParams<T> P, Tiling tl)
 {
     __shared__ int32_t s_flags[32 * VEC];
+    __shared__ int32_t s_base;
     cg::grid_group grid = cg::this_grid();
     for (int step = 0;; ++step) {
-        check_phase<T, VEC, DSEL>(P, step & 1, tl, s_flags);
+        check_phase_dyn<T, VEC, DSEL>(P, step & 1, tl, s_flags, &s_base);
         grid.sync();
-        var_phase<T, VEC>(P, step & 1, tl);
+        var_phase_dyn<T, VEC>(P, step & 1, tl, &s_base);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[1], 1ULL);
         grid.sync();
         if (*(volatile int32_t *)&P.ctrl[CTRL_REMAINING] <= 0) break;
@@ -136,7 +232,8 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? 2 : 1) k_persistent(D
 
 // lane l starts on frame l (if there is one); everything else is idle
 __global__ void k_init_batch(LaneState *st0, LaneState *st1, int32_t *unsat0, int32_t *unsat1,
-                             int32_t lanes, int64_t frames, int32_t *ctrl, unsigned long long *stats)
+                             int32_t lanes, int64_t frames, int32_t *ctrl, int32_t *work,
+                             unsigned long long *stats)
 {
     const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l < lanes) {
@@ -150,6 +247,7 @@ __global__ void k_init_batch(LaneState *st0, LaneState *st1, int32_t *unsat0, in
         unsat0[l] = 0;
         unsat1[l] = 0;
     }
+    for (int32_t i = l; i < 2 * kMaxLaneTiles; i += gridDim.x * blockDim.x) work[i] = 0;
     if (l == 0) {
         ctrl[CTRL_NEXT_FRAME] = (int32_t)min((int64_t)lanes, frames);
         ctrl[CTRL_REMAINING] = (int32_t)frames;
@@ -198,7 +296,7 @@ static DecodeParams<T> make_params(const qr_decoder *d, const void *llr, int llr
     P.frames = frames; P.maxiter = maxiter;
     P.success = success; P.iters = iters;
     P.post_out = post; P.post_out_f64 = post_dtype == QR_F64;
-    P.ctrl = d->ctrl; P.stats = d->stats;
+    P.ctrl = d->ctrl; P.stats = d->stats; P.work = d->work;
     return P;
 }
 
@@ -220,10 +318,9 @@ static int grid_for(int capacity, int32_t nxt)
     return (capacity / nxt) * nxt;
 }
 
-template <typename T, int DSEL>
+template <typename T, int DSEL, int VEC = Prec<T>::VEC>
 static int run_batch_t(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream)
 {
-    constexpr int VEC = Prec<T>::VEC;
     const Tiling tl = make_tiling<VEC>(P.lanes);
     if (d->schedule == QR_SCHED_PERSISTENT) {
         int per_sm = 0;
@@ -261,6 +358,11 @@ static int run_batch_t(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t str
 template <typename T>
 static int run_batch(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream)
 {
+    if constexpr (sizeof(T) == 4) {
+        // narrower lane vectors (more, lighter threads) -- experimental, QAMRECON_VEC=1|2
+        if (d->regular_degree == 6 && d->vec == 1) return run_batch_t<T, 6, 1>(d, P, stream);
+        if (d->regular_degree == 6 && d->vec == 2) return run_batch_t<T, 6, 2>(d, P, stream);
+    }
     switch (d->regular_degree) {
     case 6: return run_batch_t<T, 6>(d, P, stream);
     default: return run_batch_t<T, 0>(d, P, stream);
@@ -305,6 +407,7 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
         lanes = (lanes + 31) / 32 * 32;
         d->lanes = (int32_t)lanes;
         d->regular_degree = (g->bins.size() == 1 && g->bins[0].degree == 6) ? 6 : 0;
+        if (const char *v = getenv("QAMRECON_VEC")) d->vec = atoi(v);
         const size_t L = (size_t)lanes;
         QR_CUDA_CHECK(cudaMalloc(&d->c2v, (size_t)g->E * L * w));
         QR_CUDA_CHECK(cudaMalloc(&d->post, (size_t)g->N * L * w));
@@ -314,6 +417,7 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
         QR_CUDA_CHECK(cudaMalloc((void **)&d->unsat, 2 * L * sizeof(int32_t)));
         QR_CUDA_CHECK(cudaMalloc((void **)&d->ctrl, qr::CTRL_WORDS * sizeof(int32_t)));
         QR_CUDA_CHECK(cudaMalloc((void **)&d->stats, 2 * sizeof(unsigned long long)));
+        QR_CUDA_CHECK(cudaMalloc((void **)&d->work, 2 * qr::kMaxLaneTiles * sizeof(int32_t)));
         QR_CUDA_CHECK(cudaMemset(d->c2v, 0, (size_t)g->E * L * w));
         QR_CUDA_CHECK(cudaMemset(d->post, 0, (size_t)g->N * L * w));
         QR_CUDA_CHECK(cudaMemset(d->llr, 0, (size_t)g->N * L * w));
@@ -338,7 +442,7 @@ void qr_decoder_destroy(qr_decoder *d)
     cudaGetDevice(&prev);
     cudaSetDevice(d->device);
     cudaFree(d->c2v); cudaFree(d->post); cudaFree(d->llr); cudaFree(d->synd);
-    cudaFree(d->st); cudaFree(d->unsat); cudaFree(d->ctrl); cudaFree(d->stats);
+    cudaFree(d->st); cudaFree(d->unsat); cudaFree(d->ctrl); cudaFree(d->stats); cudaFree(d->work);
     cudaFree(d->pipe_buf);
     if (d->h_ctrl) cudaFreeHost(d->h_ctrl);
     if (d->h_stats) cudaFreeHost(d->h_stats);
@@ -374,7 +478,7 @@ int qr_decode_batch(qr_decoder *d, const void *d_llr, int llr_dtype, const uint8
         QR_CUDA_CHECK(cudaSetDevice(d->device));
         const int32_t lanes = (int32_t)std::min<int64_t>(d->lanes, (frames + 31) / 32 * 32);
         qr::k_init_batch<<<(lanes + 255) / 256, 256, 0, stream>>>(
-            d->st, d->st + lanes, d->unsat, d->unsat + lanes, lanes, frames, d->ctrl, d->stats);
+            d->st, d->st + lanes, d->unsat, d->unsat + lanes, lanes, frames, d->ctrl, d->work, d->stats);
         QR_CUDA_CHECK(cudaGetLastError());
         d->last_stream = stream;
         if (d->precision == QR_F64) {

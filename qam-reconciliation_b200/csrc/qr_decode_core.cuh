@@ -46,6 +46,7 @@ struct LaneState {
 };
 
 enum : int { CTRL_NEXT_FRAME = 0, CTRL_REMAINING = 1, CTRL_SNAPSHOT = 2, CTRL_WORDS = 8 };
+constexpr int kMaxLaneTiles = 1 << 15;
 
 template <typename T>
 struct DecodeParams {
@@ -73,6 +74,7 @@ struct DecodeParams {
     int32_t post_out_f64;
     // control words and counters
     int32_t *ctrl;
+    int32_t *work;              // [2][kMaxLaneTiles] row counters of the persistent kernel's work stealing
     unsigned long long *stats;  // [0] flooding iterations summed over finished frames
 };
 
@@ -610,11 +612,12 @@ QR_HD void var_item_fast(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32
 }
 
 template <typename T, int VEC, int DV, int U>
-QR_HD void run_var_fast(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t first, int32_t stride)
+QR_HD void run_var_fast(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t first, int32_t stride,
+                        int32_t n_end)
 {
     // U variables per trip (n, n+stride, ...): U*(DV+1) independent row loads in flight per thread;
     // the slot rows of the next trip are fetched while this one is summed.
-    const int32_t N = (int32_t)P.N, lanes = P.lanes;
+    const int32_t N = n_end, lanes = P.lanes;
     int32_t cur[U][DV], nxt[U][DV];
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -655,15 +658,16 @@ QR_HD void run_var_fast(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_
 
 // All variables n = first, first+stride, ... for the thread's lanes (decisions already in L).
 template <typename T, int VEC>
-QR_HD void run_var_range(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t first, int32_t stride)
+QR_HD void run_var_range(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t first, int32_t stride,
+                         int32_t n_end)
 {
     if (!(L.upd | L.fin_ok | L.fin_fail)) return;
     const bool steady = !L.fresh && !(L.fin_ok | L.fin_fail) && L.upd == L.active;
     constexpr int U = 2;  // 4 was measured slower on B200 (register spills in the persistent kernel)
-    if (steady && P.var_deg == 3) { run_var_fast<T, VEC, 3, U>(P, L, first, stride); return; }
-    if (steady && P.var_deg == 4) { run_var_fast<T, VEC, 4, U>(P, L, first, stride); return; }
-    if (steady && P.var_deg == 2) { run_var_fast<T, VEC, 2, U>(P, L, first, stride); return; }
-    for (int32_t n = first; n < P.N; n += stride) var_item<T, VEC>(P, L, n);
+    if (steady && P.var_deg == 3) { run_var_fast<T, VEC, 3, U>(P, L, first, stride, n_end); return; }
+    if (steady && P.var_deg == 4) { run_var_fast<T, VEC, 4, U>(P, L, first, stride, n_end); return; }
+    if (steady && P.var_deg == 2) { run_var_fast<T, VEC, 2, U>(P, L, first, stride, n_end); return; }
+    for (int32_t n = first; n < n_end; n += stride) var_item<T, VEC>(P, L, n);
 }
 
 }  // namespace qr

@@ -22,12 +22,14 @@ struct qr_decoder {
     int32_t lanes = 0;
     int device = 0;
     int regular_degree = 0;  // > 0: check-regular graph with a specialised kernel
+    int vec = 0;             // 0: default lanes per thread; 1 or 2: narrower (fp32 only, experimental)
     void *c2v = nullptr, *post = nullptr, *llr = nullptr;
     uint8_t *synd = nullptr;
     qr::LaneState *st = nullptr;          // [2][lanes]
     int32_t *unsat = nullptr;             // [2][lanes]
     int32_t *ctrl = nullptr;              // [CTRL_WORDS]
     unsigned long long *stats = nullptr;  // [2]
+    int32_t *work = nullptr;              // [2][kMaxLaneTiles]
     int32_t *h_ctrl = nullptr;            // pinned mirrors
     unsigned long long *h_stats = nullptr;
     cudaStream_t last_stream = nullptr;
@@ -48,4 +50,7 @@ struct qr_mapper {
     double *FY_thr = nullptr, *delta = nullptr, *fwrd = nullptr, *back = nullptr, *bare = nullptr,
            *inf_erf = nullptr;
     size_t n_table_doubles = 0;
+    double *inv_tab = nullptr;   // F_Y on a uniform grid, see MapperView
+    int32_t inv_n = 0;
+    double inv_y0 = 0, inv_h = 0;
 };

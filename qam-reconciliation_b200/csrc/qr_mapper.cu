@@ -17,6 +17,7 @@ static MapperView view_of(const qr_mapper *m)
     v.noise_var = m->noise_var; v.sigma = m->sigma; v.s2 = m->s2;
     v.constellation = m->constellation; v.thresholds = m->thresholds; v.probabilities = m->probabilities;
     v.sign_config = m->d_sign; v.FY_thr = m->FY_thr; v.delta = m->delta; v.bare = m->bare;
+    v.inv_tab = m->inv_tab; v.inv_n = m->inv_n; v.inv_y0 = m->inv_y0; v.inv_h = m->inv_h;
     return v;
 }
 
@@ -56,6 +57,13 @@ __global__ void k_mapper_tables(MapperView m, double *FY_thr, double *delta, dou
         inf_erf[0 * M + j] = -1;
         for (int i = 1; i < M; ++i) inf_erf[i * M + j] = erf((thr[i] - a[j]) / m.s2);
     }
+}
+
+// F_Y on a uniform grid (starting points of the fast inverse); one thread per grid point
+__global__ void k_fill_inv_table(MapperView m, double *tab, int32_t n, double y0, double h)
+{
+    const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) tab[j] = mixture_cdf(m.constellation, m.probabilities, m.order, m.s2, y0 + j * h);
 }
 
 struct SharedTables {
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__(128) k_demap(MapperView m, const double *__res
         for (int k = 0; k < m.bps; ++k) { N[k] = 0; D[k] = 0; }
         for (int i = 0; i < m.order; ++i) {
             const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
-            const double yh = fast ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i)
+            const double yh = fast ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i, InvTable{m.inv_tab, m.inv_n, m.inv_y0, m.inv_h})
                                    : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
             // the body of demap_from_yhat for one i (kept inline: y_hat need not be stored)
             double sum = 0;
@@ -162,7 +170,7 @@ __global__ void __launch_bounds__(128) k_g_inv(MapperView m, const double *__res
          j += (int64_t)gridDim.x * blockDim.x) {
         const int32_t i = (int32_t)region[j];
         const double target = inv_target(s.sign, s.FYt, s.delta, n_hat[j], i);
-        y_hat[j] = (mode & 1) ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i)
+        y_hat[j] = (mode & 1) ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i, InvTable{m.inv_tab, m.inv_n, m.inv_y0, m.inv_h})
                               : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
     }
 }
@@ -247,6 +255,17 @@ int qr_mapper_create(int bits_per_symbol, const double *h_constellation, const d
         else QR_CUDA_CHECK(cudaMemset(m->d_sign, 0, M));
         qr::k_mapper_tables<<<1, 32>>>(qr::view_of(m), m->FY_thr, m->delta, m->fwrd, m->back, m->bare, m->inf_erf);
         QR_CUDA_CHECK(cudaGetLastError());
+        // inverse-CDF starting table: +-9 sigma around the constellation, ~2e-3 sigma-free grid step
+        m->inv_n = 16385;
+        m->inv_y0 = h_constellation[0] - 9.0 * m->sigma;
+        m->inv_h = (h_constellation[M - 1] + 9.0 * m->sigma - m->inv_y0) / (m->inv_n - 1);
+        QR_CUDA_CHECK(cudaMalloc((void **)&m->inv_tab, m->inv_n * sizeof(double)));
+        {
+            qr::MapperView v = qr::view_of(m);
+            v.inv_tab = nullptr;
+            qr::k_fill_inv_table<<<(m->inv_n + 255) / 256, 256>>>(v, m->inv_tab, m->inv_n, m->inv_y0, m->inv_h);
+        }
+        QR_CUDA_CHECK(cudaGetLastError());
         QR_CUDA_CHECK(cudaDeviceSynchronize());
         return QR_OK;
     };
@@ -263,6 +282,7 @@ void qr_mapper_destroy(qr_mapper *m)
         qr::DeviceGuard guard(m->device);
         cudaFree(m->d_tables);
         cudaFree(m->d_sign);
+        cudaFree(m->inv_tab);
     }
     delete m;
 }

@@ -24,6 +24,16 @@ struct MapperView {
     const double *FY_thr;         // [order+1]  F_Y_thresholds
     const double *delta;          // [order]    delta_F_Y
     const double *bare;           // [order*bps]
+    // F_Y sampled on a uniform grid y = inv_y0 + j * inv_h, j < inv_n: starting points of the fast inverse
+    const double *inv_tab;
+    int32_t inv_n;
+    double inv_y0, inv_h;
+};
+
+struct InvTable {
+    const double *F;
+    int32_t n;
+    double y0, h;
 };
 
 // rounding-exact multiply/add: the reference is compiled without FMA contraction
@@ -196,11 +206,27 @@ QR_HD double norm_quantile(double q)
 // error (~1e-14) of a midpoint.  Saturated targets (<= 0 or >= 1), whose result is defined by where
 // erf rounds to +-1, take the exact path.
 QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, const double *FYt, int order,
-                        double sigma, double s2, double target, double accuracy, int32_t region)
+                        double sigma, double s2, double target, double accuracy, int32_t region,
+                        const InvTable tab)
 {
     if (!(target > 0.0 && target < 1.0)) return g_inv_exact(a, p, order, s2, target, accuracy);
     double rlo, rhi, y;
-    if (region > 0 && region < order - 1) {
+    bool presolved = false;
+    if (tab.n > 1 && target >= tab.F[0] && target < tab.F[tab.n - 1]) {
+        // table lookup: F[lo] <= target < F[hi] brackets the root within one grid step, linear
+        // interpolation lands within ~1e-5 of it -- close enough for one cubic (Halley) step
+        int32_t lo = 0, hi = tab.n - 1;
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (tab.F[mid] <= target) lo = mid; else hi = mid;
+        }
+        const double f0 = tab.F[lo], f1 = tab.F[hi];
+        rlo = tab.y0 + lo * tab.h;
+        rhi = rlo + tab.h;
+        y = rlo + (f1 > f0 ? (target - f0) / (f1 - f0) : 0.5) * tab.h;
+        rlo -= 1e-9; rhi += 1e-9;     // the table was rounded: leave the safeguard a hair of slack
+        presolved = true;
+    } else if (region > 0 && region < order - 1) {
         rlo = thr[region];
         rhi = thr[region + 1];
         const double t0 = FYt[region], t1 = FYt[region + 1];
@@ -226,6 +252,27 @@ QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, con
     }
     if (!(rlo < rhi)) return g_inv_exact(a, p, order, s2, target, accuracy);
     if (!(y > rlo && y < rhi)) y = 0.5 * (rlo + rhi);
+    // Cheap float pre-solve (3 Newton steps with erff/expf bring y within ~1e-6 of the root where the
+    // density is not tiny), so that the double-precision Halley loop below usually needs ONE
+    // evaluation: its cubic step from 1e-6 lands at ~1e-18.  Anything the float solve gets wrong
+    // (tails, flat spots) is caught by the bracket and the convergence test of the double loop.
+    if (!presolved) {
+        const float s2f = (float)s2, tf = (float)target, c0f = (float)(0.3989422804014327 / sigma);
+        float yf = (float)y;
+        const float lof = (float)rlo, hif = (float)rhi;
+        for (int it = 0; it < 3; ++it) {
+            float F = 0.f, f = 0.f;
+            for (int k = 0; k < order; ++k) {
+                const float z = (yf - (float)a[k]) / s2f;
+                F += (float)p[k] * (0.5f * (1.f + erff(z)));
+                f += (float)p[k] * expf(-z * z);
+            }
+            const float yn = yf - (F - tf) / (f * c0f);
+            if (!(yn > lof && yn < hif)) break;
+            yf = yn;
+        }
+        if ((double)yf > rlo && (double)yf < rhi) y = (double)yf;
+    }
     const double c0 = 0.3989422804014327 / sigma, c1 = c0 / (sigma * sigma);
     double root = y;
     double f = 1;
@@ -275,12 +322,28 @@ QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, con
         lo = -1; hi = 0;
         for (int it = 0; lo > root && it < kMaxDoublings; ++it) { hi = lo; lo *= 2.; }
     }
-    for (int it = 0; (hi - lo) > accuracy && it < kMaxHalvings; ++it) {
-        const double mid = (hi + lo) / 2;
-        if (mid > root) hi = mid;
-        else lo = mid;
+    // The halving loop picks, among the 2^k cells of width W / 2^k (k = halvings until the width is
+    // <= accuracy), the one with lo_cell <= root < hi_cell (a root on a boundary goes to the upper cell,
+    // root >= hi to the last, root < lo to the first).  lo, hi and every midpoint are dyadic, so the
+    // cell can be computed directly and the result is bit-identical to running the loop.
+    const double W = hi - lo;
+    int k = 0;
+    for (double wd = W; wd > accuracy && k < kMaxHalvings; wd *= 0.5) ++k;
+    if (k > 52) {   // not reachable for accuracy = 1e-9 and finite brackets; keep the loop for safety
+        for (int it = 0; (hi - lo) > accuracy && it < kMaxHalvings; ++it) {
+            const double mid = (hi + lo) / 2;
+            if (mid > root) hi = mid;
+            else lo = mid;
+        }
+        return (hi + lo) / 2;
     }
-    return (hi + lo) / 2;
+    const double cell = ldexp(W, -k), last = ldexp(1.0, k) - 1.0;
+    double idx = floor((root - lo) / cell);
+    idx = idx < 0.0 ? 0.0 : (idx > last ? last : idx);
+    // (root - lo) may have been rounded across a boundary: settle with exact comparisons
+    if (idx > 0.0 && lo + idx * cell > root) idx -= 1.0;
+    else if (idx < last && lo + (idx + 1.0) * cell <= root) idx += 1.0;
+    return lo + (idx + 0.5) * cell;
 }
 
 // demap_lappr (noisemapper.pyx:450-540) given the `order` reconstructed samples y_hat[i].

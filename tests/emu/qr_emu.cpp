@@ -57,7 +57,7 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
     P.llr_in = llr; P.llr_in_f64 = llr_dtype == QR_F64; P.synd_in = synd;
     P.frames = frames; P.maxiter = maxiter; P.success = success; P.iters = iters;
     P.post_out = post; P.post_out_f64 = post_dtype == QR_F64;
-    P.ctrl = ctrl.data(); P.stats = stats;
+    P.ctrl = ctrl.data(); P.stats = stats; P.work = nullptr;
     for (int l = 0; l < lanes; ++l) {
         LaneState s;
         s.frame = l < frames ? l : -1; s.iter = 0; s.fresh = s.frame >= 0; s.pad = 0;
@@ -93,7 +93,7 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
         for (int jv = 0; jv < LV; ++jv) {
             LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
             decide_lanes<T, VEC>(P, cur, L);
-            for (int32_t t = 0; t < 5; ++t) run_var_range<T, VEC>(P, L, t, 5);
+            for (int32_t t = 0; t < 5; ++t) run_var_range<T, VEC>(P, L, t, 5, (int32_t)g.N);
             bookkeep_lanes<T, VEC>(P, cur, L);
         }
     }
@@ -147,10 +147,16 @@ void emu_demap(int bps, const double *a, const double *thr, const double *p, dou
     for (int i = 1; i < M; ++i) FYt[i] = mixture_cdf(a, p, M, s2, thr[i]);
     for (int i = 0; i < M; ++i) delta[i] = FYt[i + 1] - FYt[i];
     std::vector<double> yh(M);
+    // the same starting table libqamrecon builds on the device (qr_mapper_create)
+    const int32_t tn = 16385;
+    const double ty0 = a[0] - 9.0 * sigma, th = (a[M - 1] + 9.0 * sigma - ty0) / (tn - 1);
+    std::vector<double> tabF(tn);
+    for (int32_t j = 0; j < tn; ++j) tabF[j] = mixture_cdf(a, p, M, s2, ty0 + j * th);
+    const InvTable tab{(mode & 4) ? nullptr : tabF.data(), (mode & 4) ? 0 : tn, ty0, th};
     for (int64_t s = 0; s < n; ++s) {
         for (int i = 0; i < M; ++i) {
             const double target = inv_target(sign, FYt.data(), delta.data(), n_hat[s], i);
-            yh[i] = (mode & 1) ? g_inv_fast(a, p, thr, FYt.data(), M, sigma, s2, target, 1e-9, i)
+            yh[i] = (mode & 1) ? g_inv_fast(a, p, thr, FYt.data(), M, sigma, s2, target, 1e-9, i, tab)
                                : g_inv_exact(a, p, M, s2, target, 1e-9);
             if (yhat_out) yhat_out[s * M + i] = yh[i];
         }
