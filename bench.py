@@ -330,9 +330,18 @@ def ours(a):
     k_ms = float(np.mean(kt))
     peak, peak_src = peaks()
     achieved = fi * bytes_per_frame_iter / (k_ms / 1e3) / 1e9
+    traffic = None
+    try:   # DRAM bytes of the same launch from the committed ncu --set full capture (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        c = tj["config"]
+        if (c["n"], c["frames"], c["max_iterations"], c["precision"]) == (n, B, MAXITER, a.precision) and \
+                a.schedule == 0 and fi == B * MAXITER:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_persistent (decoder, one launch per batch)" if a.schedule == 0
                 else "k_check+k_var", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fi * bytes_per_frame_iter, "launch_ms": k_ms,
                 "edge_updates_per_s": fi * E / (k_ms / 1e3), "frame_iterations_per_launch": fi,
                 "decode_only_frames_per_s": B / (k_ms / 1e3)}
@@ -381,7 +390,7 @@ def ours(a):
             "config": {"workload": f"(3,6)-regular LDPC n={n} R=1/2 (seed {CODE_SEED}), 4-PAM Alternating, "
                                    f"Es/N0={a.snr} dB, maxiter {MAXITER}, soft reverse reconciliation "
                                    f"(BASELINE config 2)",
-                       "frames_per_gpu_per_step": B, "demap": a.demap, "decoder_lanes": dec_lanes(dec, a),
+                       "frames_per_gpu_per_step": B, "demap": a.demap, "decoder_lanes": a.lanes or 512,
                        "schedule": "persistent" if a.schedule == 0 else "launch",
                        "l2_policy": f"{n_sets} alternating input sets of {B * S * 16 / 1e9:.1f} GB each (>> 126 MB L2)"},
             "info_gbit_per_s": value * K / 1e9,

@@ -38,6 +38,9 @@ struct qr_decoder {
     // scratch of qr_reconcile_host (grow-only)
     void *pipe_buf = nullptr;
     size_t pipe_cap = 0;
+    bool pipe_streams_ready = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host pipeline
+    cudaEvent_t ev_in[2] = {}, ev_compute[2] = {}, ev_out[2] = {}, ev_start = nullptr;
 };
 
 struct qr_mapper {

@@ -1,8 +1,15 @@
 // Whole reverse-reconciliation pass over host buffers: the chain of the reference's Monte-Carlo
 // loop body (sims/reconciliation.pyx:129-153 soft reverse, :300-308 hard reverse, :214-227 direct)
 // for a batch of frames, host -> device -> host inside one call.
+//
+// The batch is cut into chunks that flow through a three-stage pipeline on three streams --
+// host-to-device copy of chunk c+1, kernels of chunk c, device-to-host copy of chunk c-1 -- with
+// two sets of device buffers, so with pinned host memory the PCIe transfers hide behind the
+// decoder.  The decoder workspace is shared: kernels of consecutive chunks serialise on the
+// caller's stream.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "qr_handles.h"
@@ -75,47 +82,88 @@ extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, in
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     qr::DeviceGuard guard(d->device);
 
+    // chunking: at least two decoder fills per chunk, about eight chunks per batch
+    int64_t chunk = std::max<int64_t>(2 * (int64_t)d->lanes, (frames + 7) / 8);
+    chunk = std::min(chunk, frames);
+    const int64_t n_chunks = (frames + chunk - 1) / chunk;
+    const int n_sets = n_chunks > 1 ? 2 : 1;
+
+    if (!d->pipe_streams_ready) {
+        QR_CUDA_CHECK(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
+        QR_CUDA_CHECK(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            QR_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_in[i], cudaEventDisableTiming));
+            QR_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_compute[i], cudaEventDisableTiming));
+            QR_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_out[i], cudaEventDisableTiming));
+        }
+        QR_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming));
+        d->pipe_streams_ready = true;
+    }
+
     Carver sizing(nullptr);
-    carve(sizing, frames, S, N, C, wl, wp);
+    for (int s = 0; s < n_sets; ++s) carve(sizing, chunk, S, N, C, wl, wp);
     const size_t need = sizing.off + 256;
     if (need > d->pipe_cap) {
-        QR_CUDA_CHECK(cudaStreamSynchronize(st));
+        QR_CUDA_CHECK(cudaDeviceSynchronize());
         cudaFree(d->pipe_buf);
         d->pipe_buf = nullptr;
         d->pipe_cap = 0;
         QR_CUDA_CHECK(cudaMalloc(&d->pipe_buf, need));
         d->pipe_cap = need;
     }
-    Carver c(d->pipe_buf);
-    Buffers b = carve(c, frames, S, N, C, wl, wp);
+    Carver carver(d->pipe_buf);
+    Buffers sets[2];
+    for (int s = 0; s < n_sets; ++s) sets[s] = carve(carver, chunk, S, N, C, wl, wp);
 
-    QR_CUDA_CHECK(cudaMemcpyAsync(b.y, h_y, frames * S * sizeof(double), cudaMemcpyHostToDevice, st));
-    QR_CUDA_CHECK(cudaMemcpyAsync(b.tx, h_tx_index, frames * S * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    int rc;
-    if (mode == 0) {
-        if ((rc = qr_front_end(m, b.y, frames * S, b.idx, b.n_hat, b.word, st))) return rc;
-        if ((rc = qr_eval_syndrome(g, b.word, b.synd, frames, st))) return rc;
-        if ((rc = qr_demap_lappr(m, b.n_hat, b.tx, frames * S, demap_mode, alpha, b.llr, llr_dtype, st))) return rc;
-    } else if (mode == 1) {
-        if ((rc = qr_front_end(m, b.y, frames * S, b.idx, nullptr, b.word, st))) return rc;
-        if ((rc = qr_eval_syndrome(g, b.word, b.synd, frames, st))) return rc;
-        if ((rc = qr_bare_llr(m, b.tx, frames * S, b.llr, llr_dtype, st))) return rc;
-    } else {
-        if ((rc = qr_symbols_to_bits(m, b.tx, frames * S, b.word, st))) return rc;
-        if ((rc = qr_eval_syndrome(g, b.word, b.synd, frames, st))) return rc;
-        if ((rc = qr_direct_llr(m, b.y, frames * S, 2 * m->noise_var, b.llr, llr_dtype, st))) return rc;
+    // work queued on the caller's stream before this call must precede our copies
+    QR_CUDA_CHECK(cudaEventRecord(d->ev_start, st));
+    QR_CUDA_CHECK(cudaStreamWaitEvent(d->s_in, d->ev_start, 0));
+    QR_CUDA_CHECK(cudaStreamWaitEvent(d->s_out, d->ev_start, 0));
+
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int s = (int)(c % n_sets);
+        const Buffers &b = sets[s];
+        const int64_t f0 = c * chunk, nf = std::min(chunk, frames - f0);
+        // stage 1: inputs of chunk c (the set is free once the kernels of chunk c-2 are done)
+        if (c >= n_sets) QR_CUDA_CHECK(cudaStreamWaitEvent(d->s_in, d->ev_compute[s], 0));
+        QR_CUDA_CHECK(cudaMemcpyAsync(b.y, h_y + f0 * S, nf * S * sizeof(double), cudaMemcpyHostToDevice, d->s_in));
+        QR_CUDA_CHECK(cudaMemcpyAsync(b.tx, h_tx_index + f0 * S, nf * S * sizeof(int64_t), cudaMemcpyHostToDevice, d->s_in));
+        QR_CUDA_CHECK(cudaEventRecord(d->ev_in[s], d->s_in));
+        // stage 2: kernels (outputs of the set are free once chunk c-2 has been copied out)
+        QR_CUDA_CHECK(cudaStreamWaitEvent(st, d->ev_in[s], 0));
+        if (c >= n_sets) QR_CUDA_CHECK(cudaStreamWaitEvent(st, d->ev_out[s], 0));
+        int rc;
+        if (mode == 0) {
+            if ((rc = qr_front_end(m, b.y, nf * S, b.idx, b.n_hat, b.word, st))) return rc;
+            if ((rc = qr_eval_syndrome(g, b.word, b.synd, nf, st))) return rc;
+            if ((rc = qr_demap_lappr(m, b.n_hat, b.tx, nf * S, demap_mode, alpha, b.llr, llr_dtype, st))) return rc;
+        } else if (mode == 1) {
+            if ((rc = qr_front_end(m, b.y, nf * S, b.idx, nullptr, b.word, st))) return rc;
+            if ((rc = qr_eval_syndrome(g, b.word, b.synd, nf, st))) return rc;
+            if ((rc = qr_bare_llr(m, b.tx, nf * S, b.llr, llr_dtype, st))) return rc;
+        } else {
+            if ((rc = qr_symbols_to_bits(m, b.tx, nf * S, b.word, st))) return rc;
+            if ((rc = qr_eval_syndrome(g, b.word, b.synd, nf, st))) return rc;
+            if ((rc = qr_direct_llr(m, b.y, nf * S, 2 * m->noise_var, b.llr, llr_dtype, st))) return rc;
+        }
+        if ((rc = qr_decode_batch(d, b.llr, llr_dtype, b.synd, nf, max_iterations, b.success, b.iters, b.post,
+                                  post_dtype, st)))
+            return rc;
+        if (h_bit_errors && (rc = qr_count_errors(b.post, post_dtype, b.word, nf, N, k_info, b.errors, st))) return rc;
+        QR_CUDA_CHECK(cudaEventRecord(d->ev_compute[s], st));
+        // stage 3: results of chunk c
+        QR_CUDA_CHECK(cudaStreamWaitEvent(d->s_out, d->ev_compute[s], 0));
+        if (h_bit_errors)
+            QR_CUDA_CHECK(cudaMemcpyAsync(h_bit_errors + f0, b.errors, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, d->s_out));
+        if (h_success) QR_CUDA_CHECK(cudaMemcpyAsync(h_success + f0, b.success, nf, cudaMemcpyDeviceToHost, d->s_out));
+        if (h_iters) QR_CUDA_CHECK(cudaMemcpyAsync(h_iters + f0, b.iters, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, d->s_out));
+        if (h_post)
+            QR_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(h_post) + (size_t)f0 * N * wp, b.post, (size_t)nf * N * wp,
+                                          cudaMemcpyDeviceToHost, d->s_out));
+        if (h_word) QR_CUDA_CHECK(cudaMemcpyAsync(h_word + f0 * N, b.word, nf * N, cudaMemcpyDeviceToHost, d->s_out));
+        QR_CUDA_CHECK(cudaEventRecord(d->ev_out[s], d->s_out));
     }
-    if ((rc = qr_decode_batch(d, b.llr, llr_dtype, b.synd, frames, max_iterations, b.success, b.iters, b.post,
-                              post_dtype, st)))
-        return rc;
-    if (h_bit_errors) {
-        if ((rc = qr_count_errors(b.post, post_dtype, b.word, frames, N, k_info, b.errors, st))) return rc;
-        QR_CUDA_CHECK(cudaMemcpyAsync(h_bit_errors, b.errors, frames * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    }
-    if (h_success) QR_CUDA_CHECK(cudaMemcpyAsync(h_success, b.success, frames, cudaMemcpyDeviceToHost, st));
-    if (h_iters) QR_CUDA_CHECK(cudaMemcpyAsync(h_iters, b.iters, frames * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (h_post) QR_CUDA_CHECK(cudaMemcpyAsync(h_post, b.post, frames * N * wp, cudaMemcpyDeviceToHost, st));
-    if (h_word) QR_CUDA_CHECK(cudaMemcpyAsync(h_word, b.word, frames * N, cudaMemcpyDeviceToHost, st));
+    QR_CUDA_CHECK(cudaStreamSynchronize(d->s_out));
     QR_CUDA_CHECK(cudaStreamSynchronize(st));
     return QR_OK;
 }
