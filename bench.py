@@ -115,13 +115,15 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arms
-def _cpu_worker(args):
-    """One process, one frame at a time (the north star's CPU protocol).  kind: 'port' (oracle C
-    restatement) or 'reference' (compiled reference in oracle/_ref)."""
-    kind, n, snr, seeds, demap_div = args
-    import numpy as np
-    t_setup = time.time()
+_W = {}
+
+
+def _cpu_init(kind, n, snr):
+    """Per worker process, once: build the code, the decoder (the reference's constructor is quadratic:
+    ~40-100 s at n = 64800) and the mapper.  kind: 'port' (oracle C restatement) or 'reference'
+    (compiled reference in oracle/_ref)."""
     import importlib.util
+    t_setup = time.time()
     spec = importlib.util.spec_from_file_location("qr_codes", os.path.join(PKG, "qamreconciliation", "codes.py"))
     codes = importlib.util.module_from_spec(spec)     # the product's numpy-only code generator
     spec.loader.exec_module(codes)
@@ -141,9 +143,15 @@ def _cpu_worker(args):
         NM = orc.NoiseMapper
     cfg = np.zeros(1 << BPS, dtype=np.uint8); cfg[1::2] = 1
     n0 = pa.variance * 10 ** (-snr / 10) / 2
-    nm = NM(pa, n0, cfg)
-    a = np.asarray(pa.constellation)
-    t_setup = time.time() - t_setup
+    _W.update(kind=kind, n=n, n0=n0, cfg=cfg, pa=pa, dec=dec, mat=mat, nm=NM(pa, n0, cfg),
+              a=np.asarray(pa.constellation), setup=time.time() - t_setup, onm=None)
+
+
+def _cpu_step(args):
+    """One frame at a time through the whole chain (the north star's CPU protocol)."""
+    seeds, demap_div = args
+    W = _W
+    n, n0, pa, nm, dec, mat, a = W["n"], W["n0"], W["pa"], W["nm"], W["dec"], W["mat"], W["a"]
     S = n // BPS
     t_chain = t_demap = t_dec = 0.0
     iters = 0
@@ -164,9 +172,10 @@ def _cpu_worker(args):
         t2 = time.time()
         if demap_div > 1:
             # the decoder needs LLRs for the whole frame: the oracle port supplies the rest (untimed)
-            from oracle import port as orc2
-            onm = orc2.NoiseMapper(orc2.PAMAlphabet(BPS, 2), n0, cfg)
-            lap = np.concatenate([lap_part, onm.demap_lappr_array(nh[sub:], x[sub:])])
+            if W["onm"] is None:
+                from oracle import port as orc2
+                W["onm"] = orc2.NoiseMapper(orc2.PAMAlphabet(BPS, 2), n0, W["cfg"])
+            lap = np.concatenate([lap_part, W["onm"].demap_lappr_array(nh[sub:], x[sub:])])
         else:
             lap = lap_part
         t3 = time.time()
@@ -174,26 +183,45 @@ def _cpu_worker(args):
         t4 = time.time()
         t_chain += t1 - t0; t_demap += (t2 - t1) * demap_div; t_dec += t4 - t3
         iters += int(it)
-    return dict(setup=t_setup, chain=t_chain, demap=t_demap, dec=t_dec, frames=len(seeds), iters=iters)
+    return dict(setup=W["setup"], chain=t_chain, demap=t_demap, dec=t_dec, frames=len(seeds), iters=iters)
+
+
+class CpuArm:
+    """A pool of worker processes, each with its own decoder, reused across steps."""
+
+    def __init__(self, kind, n, snr, workers=None):
+        import multiprocessing as mp
+        self.P = workers or os.cpu_count() or 1
+        self.pool = mp.get_context("spawn").Pool(self.P, initializer=_cpu_init, initargs=(kind, n, snr))
+        self.step_no = 0
+
+    def step(self, frames_per_worker, demap_div):
+        jobs = [([100000 * self.step_no + 1000 * w + f for f in range(frames_per_worker)], demap_div)
+                for w in range(self.P)]
+        self.step_no += 1
+        t0 = time.time()
+        res = self.pool.map(_cpu_step, jobs, chunksize=1)
+        wall = time.time() - t0
+        per_frame = [(r["chain"] + r["demap"] + r["dec"]) / r["frames"] for r in res]
+        # every worker runs concurrently on its own core: aggregate rate = sum of per-worker rates
+        return dict(fps=sum(1.0 / t for t in per_frame), cores=self.P, wall=wall,
+                    setup=max(r["setup"] for r in res),
+                    chain=float(np.mean([r["chain"] / r["frames"] for r in res])),
+                    demap=float(np.mean([r["demap"] / r["frames"] for r in res])),
+                    dec=float(np.mean([r["dec"] / r["frames"] for r in res])),
+                    iters=float(np.mean([r["iters"] / r["frames"] for r in res])))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def run_cpu(kind, n, snr, frames_per_worker, demap_div, workers=None):
-    import multiprocessing as mp
-    P = workers or os.cpu_count() or 1
-    ctx = mp.get_context("spawn")
-    jobs = [(kind, n, snr, [1000 * w + f for f in range(frames_per_worker)], demap_div) for w in range(P)]
-    t0 = time.time()
-    with ctx.Pool(P) as pool:
-        res = pool.map(_cpu_worker, jobs)
-    wall = time.time() - t0
-    per_frame = [(r["chain"] + r["demap"] + r["dec"]) / r["frames"] for r in res]
-    # every worker runs concurrently on its own core: aggregate rate = sum of per-worker rates
-    fps = sum(1.0 / t for t in per_frame)
-    return dict(fps=fps, cores=P, wall=wall, setup=max(r["setup"] for r in res),
-                chain=float(np.mean([r["chain"] / r["frames"] for r in res])),
-                demap=float(np.mean([r["demap"] / r["frames"] for r in res])),
-                dec=float(np.mean([r["dec"] / r["frames"] for r in res])),
-                iters=float(np.mean([r["iters"] / r["frames"] for r in res])))
+    arm = CpuArm(kind, n, snr, workers)
+    try:
+        return arm.step(frames_per_worker, demap_div)
+    finally:
+        arm.close()
 
 
 def reference_arm(a):
@@ -206,9 +234,9 @@ def reference_arm(a):
     # The reference's demap_lappr_array costs ~27 s per n=64800 frame (Python-level scipy.erf per call):
     # it is timed on the first 1/16 of each frame's symbols and scaled by 16, everything else on whole frames.
     div = 16 if kind == "reference" else 1
-    results = []
-    for _ in range(a.warmup + a.steps):
-        results.append(run_cpu(kind, a.n, a.snr, 1, div))
+    arm = CpuArm(kind, a.n, a.snr)
+    results = [arm.step(1, div) for _ in range(a.warmup + a.steps)]
+    arm.close()
     res = results[a.warmup:] or results
     fps = float(np.mean([r["fps"] for r in res]))
     ms = float(np.mean([1000.0 * r["cores"] / r["fps"] for r in res]))
@@ -220,9 +248,7 @@ def reference_arm(a):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"(3,6)-regular LDPC n={a.n} R=1/2, 4-PAM Alternating, Es/N0={a.snr} dB, "
-                                   f"maxiter {MAXITER}, soft reverse reconciliation",
-                       "frames_per_step": res[0]["cores"]},
+            "config": {"workload": workload_name(a.n, a.snr), "frames_per_step": res[0]["cores"]},
             "info_gbit_per_s": fps * K / 1e9,
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": res[0]["cores"], "kind": kind, "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -387,9 +413,7 @@ def ours(a):
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f64", "data": "synthetic",
-            "config": {"workload": f"(3,6)-regular LDPC n={n} R=1/2 (seed {CODE_SEED}), 4-PAM Alternating, "
-                                   f"Es/N0={a.snr} dB, maxiter {MAXITER}, soft reverse reconciliation "
-                                   f"(BASELINE config 2)",
+            "config": {"workload": workload_name(n, a.snr),
                        "frames_per_gpu_per_step": B, "demap": a.demap, "decoder_lanes": a.lanes or 512,
                        "schedule": "persistent" if a.schedule == 0 else "launch",
                        "l2_policy": f"{n_sets} alternating input sets of {B * S * 16 / 1e9:.1f} GB each (>> 126 MB L2)"},
@@ -402,8 +426,9 @@ def ours(a):
         dist.destroy_process_group()
 
 
-def dec_lanes(dec, a):
-    return a.lanes or "library default (L2-sized)"
+def workload_name(n, snr):
+    return (f"(3,6)-regular LDPC n={n} R=1/2 (seed {CODE_SEED}), 4-PAM Alternating, Es/N0={snr} dB, "
+            f"maxiter {MAXITER}, soft reverse reconciliation (BASELINE config 2)")
 
 
 if __name__ == "__main__":
