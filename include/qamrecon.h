@@ -160,6 +160,21 @@ int qr_bare_llr(const qr_mapper *m, const int64_t *d_tx_index, int64_t n, void *
 int qr_direct_llr(const qr_mapper *m, const double *d_y, int64_t n, double two_variance,
                   void *d_llr, int llr_dtype, void *stream);
 
+/* ---------------------------------------------------------------- whole path, device buffers
+ * The chain of sims/reconciliation.pyx:129-153 (mode 0 soft reverse, 1 hard reverse :300-308,
+ * 2 soft direct :214-227) for `frames` frames whose channel outputs d_y [frames][S] and Alice's
+ * symbols d_tx_index [frames][S] are already in device memory.  Outputs (device; d_post, d_word,
+ * d_synd, d_bit_errors may be NULL): success, iters, post [frames][N], word [frames][N] (the bits the
+ * syndrome was taken of), synd [frames][C], bit_errors[frames] over the first k_info bits.
+ * One call, all kernels enqueued back to back on `stream`; results are identical to calling
+ * qr_front_end / qr_eval_syndrome / qr_demap_lappr / qr_decode_batch / qr_count_errors one after the
+ * other (intermediate arrays live in scratch owned by the decoder handle). */
+int qr_reconcile_device(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha,
+                        const double *d_y, const int64_t *d_tx_index, int64_t frames,
+                        int32_t max_iterations, int64_t k_info, uint8_t *d_success, int32_t *d_iters,
+                        void *d_post, int post_dtype, uint8_t *d_word, uint8_t *d_synd,
+                        int32_t *d_bit_errors, void *stream);
+
 /* ---------------------------------------------------------------- whole path, host buffers
  * One reverse-reconciliation pass over `frames` frames held in HOST memory (pinned memory makes
  * the copies asynchronous), the chain of sims/reconciliation.pyx:129-153:

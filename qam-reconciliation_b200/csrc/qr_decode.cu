@@ -444,6 +444,7 @@ void qr_decoder_destroy(qr_decoder *d)
     cudaFree(d->c2v); cudaFree(d->post); cudaFree(d->llr); cudaFree(d->synd);
     cudaFree(d->st); cudaFree(d->unsat); cudaFree(d->ctrl); cudaFree(d->stats); cudaFree(d->work);
     cudaFree(d->pipe_buf);
+    cudaFree(d->dev_buf);
     if (d->pipe_streams_ready) {
         cudaStreamDestroy(d->s_in); cudaStreamDestroy(d->s_out);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(d->ev_in[i]); cudaEventDestroy(d->ev_compute[i]); cudaEventDestroy(d->ev_out[i]); }

@@ -4,6 +4,10 @@
 #include <cuda_runtime.h>
 
 #include "qr_common.h"
+#include "qr_mapper_core.cuh"
+
+struct qr_mapper;
+struct qr_decoder;
 
 namespace qr {
 struct LaneState;
@@ -13,6 +17,10 @@ struct DeviceGuard {
     explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
     ~DeviceGuard() { cudaSetDevice(prev); }
 };
+}  // namespace qr
+
+namespace qr {
+MapperView mapper_view(const qr_mapper *m);
 }  // namespace qr
 
 struct qr_decoder {
@@ -38,6 +46,8 @@ struct qr_decoder {
     // scratch of qr_reconcile_host (grow-only)
     void *pipe_buf = nullptr;
     size_t pipe_cap = 0;
+    void *dev_buf = nullptr;   // scratch of qr_reconcile_device (grow-only)
+    size_t dev_cap = 0;
     bool pipe_streams_ready = false;
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host pipeline
     cudaEvent_t ev_in[2] = {}, ev_compute[2] = {}, ev_out[2] = {}, ev_start = nullptr;

@@ -7,6 +7,7 @@
 
 #include "qr_handles.h"
 #include "qr_mapper_core.cuh"
+#include "qr_mapper_device.cuh"
 
 namespace qr {
 
@@ -20,6 +21,8 @@ static MapperView view_of(const qr_mapper *m)
     v.inv_tab = m->inv_tab; v.inv_n = m->inv_n; v.inv_y0 = m->inv_y0; v.inv_h = m->inv_h;
     return v;
 }
+
+MapperView mapper_view(const qr_mapper *m) { return view_of(m); }
 
 // NoiseMapper.__cinit__ tables (noisemapper.pyx:149-235), one thread: tiny and done once
 __global__ void k_mapper_tables(MapperView m, double *FY_thr, double *delta, double *fwrd, double *back,
@@ -66,26 +69,6 @@ __global__ void k_fill_inv_table(MapperView m, double *tab, int32_t n, double y0
     if (j < n) tab[j] = mixture_cdf(m.constellation, m.probabilities, m.order, m.s2, y0 + j * h);
 }
 
-struct SharedTables {
-    double a[kMaxOrder], p[kMaxOrder], thr[kMaxOrder + 1], FYt[kMaxOrder + 1], delta[kMaxOrder];
-    uint8_t sign[kMaxOrder];
-};
-
-__device__ __forceinline__ void stage_tables(const MapperView &m, SharedTables &s)
-{
-    for (int i = threadIdx.x; i < m.order; i += blockDim.x) {
-        s.a[i] = m.constellation[i];
-        s.p[i] = m.probabilities[i];
-        s.delta[i] = m.delta[i];
-        s.sign[i] = m.sign_config[i];
-    }
-    for (int i = threadIdx.x; i <= m.order; i += blockDim.x) {
-        s.thr[i] = m.thresholds[i];
-        s.FYt[i] = m.FY_thr[i];
-    }
-    __syncthreads();
-}
-
 // hard decision (+ softening metric) (+ Gray bits) in one pass over y
 // (noisemapper.pyx:349-359, :373-388; alphabet.pyx:98-107).  idx_in != NULL: use the given indices
 // instead of deciding (map_noise / demap_symbols_to_bits on caller-provided indices).
@@ -119,44 +102,12 @@ __global__ void __launch_bounds__(128) k_demap(MapperView m, const double *__res
 {
     __shared__ SharedTables s;
     stage_tables(m, s);
-    const bool fast = (mode & 1) != 0, corrected = (mode & QR_DEMAP_CORRECTED) != 0;
-    const double two_s2 = 2 * m.noise_var;
+    const TablesRef t = tables_ref(s);
     for (int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sidx < n;
          sidx += (int64_t)gridDim.x * blockDim.x) {
-        const double nv = n_hat[sidx];
-        const int32_t j = (int32_t)tx[sidx];
-        double N[kMaxBps], D[kMaxBps];
-        for (int k = 0; k < m.bps; ++k) { N[k] = 0; D[k] = 0; }
-        for (int i = 0; i < m.order; ++i) {
-            const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
-            const double yh = fast ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i, InvTable{m.inv_tab, m.inv_n, m.inv_y0, m.inv_h})
-                                   : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
-            // the body of demap_from_yhat for one i (kept inline: y_hat need not be stored)
-            double sum = 0;
-            for (int k = 0; k < j; ++k) {
-                double ex = mul_rn(add_rn(add_rn(mul_rn(2, yh), -s.a[k]), -s.a[j]), add_rn(s.a[k], -s.a[j]));
-                if (corrected) ex = ex / two_s2;
-                sum = add_rn(sum, mul_rn(exp(ex), s.p[k]));
-            }
-            sum = add_rn(sum, s.p[j]);
-            for (int k = j + 1; k < m.order; ++k) {
-                const double ex =
-                    mul_rn(add_rn(add_rn(mul_rn(2, yh), -s.a[k]), -s.a[j]), add_rn(s.a[k], -s.a[j])) / two_s2;
-                sum = add_rn(sum, mul_rn(exp(ex), s.p[k]));
-            }
-            const double w = s.delta[i] / sum;
-            int q = i;
-            for (int k = 0; k < m.bps; ++k) {
-                if ((q * (q + 1)) & 3) D[k] = add_rn(D[k], w);
-                else N[k] = add_rn(N[k], w);
-                q >>= 1;
-            }
-        }
-        for (int k = 0; k < m.bps; ++k) {
-            double v = log(N[k]) - log(D[k]);
-            if (alpha != 1.0) v = mul_rn(v, alpha);  // sims/reconciliation.pyx:144-145
-            llr[sidx * m.bps + k] = (OUT)v;
-        }
+        double out[kMaxBps];
+        demap_symbol(m, t, n_hat[sidx], (int32_t)tx[sidx], mode, alpha, out);
+        for (int k = 0; k < m.bps; ++k) llr[sidx * m.bps + k] = (OUT)out[k];
     }
 }
 

@@ -378,6 +378,54 @@ QR_HD void demap_from_yhat(const double *a, const double *p, const double *delta
     for (int k = 0; k < bps; ++k) lappr[k] = log(N[k]) - log(D[k]);
 }
 
+// The small per-alphabet tables a kernel works from (shared memory on the device, plain arrays on
+// the host).
+struct TablesRef {
+    const double *a, *p, *thr, *FYt, *delta;
+    const uint8_t *sign;
+};
+
+// demap_lappr (noisemapper.pyx:450-540) for ONE symbol: Bob's metric n_hat, Alice's symbol j -> bps
+// LLRs (scaled by alpha, sims/reconciliation.pyx:144-145).  mode: QR_DEMAP_* bits.
+QR_HD void demap_symbol(const MapperView &m, const TablesRef &s, double nv, int32_t j, int mode, double alpha,
+                        double *out)
+{
+    const bool fast = (mode & 1) != 0, corrected = (mode & QR_DEMAP_CORRECTED) != 0;
+    const double two_s2 = 2 * m.noise_var;
+    double N[kMaxBps], D[kMaxBps];
+    for (int k = 0; k < m.bps; ++k) { N[k] = 0; D[k] = 0; }
+    for (int i = 0; i < m.order; ++i) {
+        const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
+        const double yh = fast ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i,
+                                            InvTable{m.inv_tab, m.inv_n, m.inv_y0, m.inv_h})
+                               : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
+        double sum = 0;
+        for (int k = 0; k < j; ++k) {
+            double ex = mul_rn(add_rn(add_rn(mul_rn(2, yh), -s.a[k]), -s.a[j]), add_rn(s.a[k], -s.a[j]));
+            if (corrected) ex = ex / two_s2;
+            sum = add_rn(sum, mul_rn(exp(ex), s.p[k]));
+        }
+        sum = add_rn(sum, s.p[j]);
+        for (int k = j + 1; k < m.order; ++k) {
+            const double ex =
+                mul_rn(add_rn(add_rn(mul_rn(2, yh), -s.a[k]), -s.a[j]), add_rn(s.a[k], -s.a[j])) / two_s2;
+            sum = add_rn(sum, mul_rn(exp(ex), s.p[k]));
+        }
+        const double w = s.delta[i] / sum;
+        int q = i;
+        for (int k = 0; k < m.bps; ++k) {
+            if ((q * (q + 1)) & 3) D[k] = add_rn(D[k], w);
+            else N[k] = add_rn(N[k], w);
+            q >>= 1;
+        }
+    }
+    for (int k = 0; k < m.bps; ++k) {
+        double v = log(N[k]) - log(D[k]);
+        if (alpha != 1.0) v = mul_rn(v, alpha);
+        out[k] = v;
+    }
+}
+
 // direct-reconciliation LLR (sims/reconciliation.pyx:25-51)
 QR_HD void direct_llr(const double *a, int order, int bps, double two_variance, double y, double *lappr)
 {

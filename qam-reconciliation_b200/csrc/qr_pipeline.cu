@@ -55,7 +55,83 @@ Buffers carve(Carver &c, int64_t frames, int64_t S, int64_t N, int64_t C, size_t
     return b;
 }
 
+// kernels of one chunk: y/tx (device) -> word, synd, llr -> decode -> (errors)
+int run_chain(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha, const double *y,
+              const int64_t *tx, int64_t nf, int64_t S, int32_t max_iterations, int64_t k_info, double *n_hat,
+              uint8_t *word, uint8_t *synd, void *llr, int llr_dtype, uint8_t *success, int32_t *iters, void *post,
+              int post_dtype, int32_t *errors, cudaStream_t st)
+{
+    const qr_graph *g = d->g;
+    int rc;
+    if (mode == 0) {
+        if ((rc = qr_front_end(m, y, nf * S, nullptr, n_hat, word, st))) return rc;
+        if ((rc = qr_eval_syndrome(g, word, synd, nf, st))) return rc;
+        if ((rc = qr_demap_lappr(m, n_hat, tx, nf * S, demap_mode, alpha, llr, llr_dtype, st))) return rc;
+    } else if (mode == 1) {
+        if ((rc = qr_front_end(m, y, nf * S, nullptr, nullptr, word, st))) return rc;
+        if ((rc = qr_eval_syndrome(g, word, synd, nf, st))) return rc;
+        if ((rc = qr_bare_llr(m, tx, nf * S, llr, llr_dtype, st))) return rc;
+    } else {
+        if ((rc = qr_symbols_to_bits(m, tx, nf * S, word, st))) return rc;
+        if ((rc = qr_eval_syndrome(g, word, synd, nf, st))) return rc;
+        if ((rc = qr_direct_llr(m, y, nf * S, 2 * m->noise_var, llr, llr_dtype, st))) return rc;
+    }
+    if ((rc = qr_decode_batch(d, llr, llr_dtype, synd, nf, max_iterations, success, iters, post, post_dtype, st)))
+        return rc;
+    if (errors && (rc = qr_count_errors(post, post_dtype, word, nf, g->N, k_info, errors, st))) return rc;
+    return QR_OK;
+}
+
 }  // namespace
+
+extern "C" int qr_reconcile_device(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha,
+                                   const double *d_y, const int64_t *d_tx_index, int64_t frames,
+                                   int32_t max_iterations, int64_t k_info, uint8_t *d_success, int32_t *d_iters,
+                                   void *d_post, int post_dtype, uint8_t *d_word, uint8_t *d_synd,
+                                   int32_t *d_bit_errors, void *stream_)
+{
+    if (!d || !m) return qr::fail(QR_ERR_INVALID, "null handle");
+    if (mode < 0 || mode > 2) return qr::fail(QR_ERR_INVALID, "reconciliation mode must be 0, 1 or 2");
+    if (frames < 0) return qr::fail(QR_ERR_INVALID, "bad frame count");
+    if (d->device != m->device) return qr::fail(QR_ERR_INVALID, "decoder and mapper live on different devices");
+    const qr_graph *g = d->g;
+    const int64_t N = g->N, C = g->C;
+    if (N % m->bps) return qr::fail(QR_ERR_INVALID, "codeword length is not a multiple of bits per symbol");
+    if (k_info < 0 || k_info > N) return qr::fail(QR_ERR_INVALID, "bad information length");
+    if (d_post && post_dtype != QR_F32 && post_dtype != QR_F64) return qr::fail(QR_ERR_INVALID, "bad dtype");
+    if (frames == 0) return QR_OK;
+    if (!d_y || !d_tx_index || !d_success || !d_iters) return qr::fail(QR_ERR_INVALID, "null array");
+    const int64_t S = N / m->bps;
+    const int llr_dtype = d->precision == QR_F64 ? QR_F64 : QR_F32;
+    const size_t wl = llr_dtype == QR_F64 ? 8 : 4;
+    if (!d_post) post_dtype = llr_dtype;
+    const size_t wp = post_dtype == QR_F64 ? 8 : 4;
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    qr::DeviceGuard guard(d->device);
+    // scratch: n_hat, llr, and whatever output the caller did not ask for
+    Carver sizing(nullptr);
+    auto layout = [&](Carver &c, double *&n_hat, void *&llr, uint8_t *&word, uint8_t *&synd, void *&post) {
+        n_hat = c.take<double>(frames * S);
+        llr = c.take<char>(frames * N * wl);
+        word = d_word ? d_word : c.take<uint8_t>(frames * N);
+        synd = d_synd ? d_synd : c.take<uint8_t>(frames * C);
+        post = d_post ? d_post : (d_bit_errors ? (void *)c.take<char>(frames * N * wp) : nullptr);
+    };
+    double *n_hat; void *llr, *post; uint8_t *word, *synd;
+    layout(sizing, n_hat, llr, word, synd, post);
+    const size_t need = sizing.off + 256;
+    if (need > d->dev_cap) {
+        QR_CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(d->dev_buf);
+        d->dev_buf = nullptr; d->dev_cap = 0;
+        QR_CUDA_CHECK(cudaMalloc(&d->dev_buf, need));
+        d->dev_cap = need;
+    }
+    Carver carver(d->dev_buf);
+    layout(carver, n_hat, llr, word, synd, post);
+    return run_chain(d, m, mode, demap_mode, alpha, d_y, d_tx_index, frames, S, max_iterations, k_info, n_hat, word,
+                     synd, llr, llr_dtype, d_success, d_iters, post, post_dtype, d_bit_errors, st);
+}
 
 extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha,
                                  const double *h_y, const int64_t *h_tx_index, int64_t frames,
@@ -132,24 +208,10 @@ extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, in
         // stage 2: kernels (outputs of the set are free once chunk c-2 has been copied out)
         QR_CUDA_CHECK(cudaStreamWaitEvent(st, d->ev_in[s], 0));
         if (c >= n_sets) QR_CUDA_CHECK(cudaStreamWaitEvent(st, d->ev_out[s], 0));
-        int rc;
-        if (mode == 0) {
-            if ((rc = qr_front_end(m, b.y, nf * S, b.idx, b.n_hat, b.word, st))) return rc;
-            if ((rc = qr_eval_syndrome(g, b.word, b.synd, nf, st))) return rc;
-            if ((rc = qr_demap_lappr(m, b.n_hat, b.tx, nf * S, demap_mode, alpha, b.llr, llr_dtype, st))) return rc;
-        } else if (mode == 1) {
-            if ((rc = qr_front_end(m, b.y, nf * S, b.idx, nullptr, b.word, st))) return rc;
-            if ((rc = qr_eval_syndrome(g, b.word, b.synd, nf, st))) return rc;
-            if ((rc = qr_bare_llr(m, b.tx, nf * S, b.llr, llr_dtype, st))) return rc;
-        } else {
-            if ((rc = qr_symbols_to_bits(m, b.tx, nf * S, b.word, st))) return rc;
-            if ((rc = qr_eval_syndrome(g, b.word, b.synd, nf, st))) return rc;
-            if ((rc = qr_direct_llr(m, b.y, nf * S, 2 * m->noise_var, b.llr, llr_dtype, st))) return rc;
-        }
-        if ((rc = qr_decode_batch(d, b.llr, llr_dtype, b.synd, nf, max_iterations, b.success, b.iters, b.post,
-                                  post_dtype, st)))
-            return rc;
-        if (h_bit_errors && (rc = qr_count_errors(b.post, post_dtype, b.word, nf, N, k_info, b.errors, st))) return rc;
+        int rc = run_chain(d, m, mode, demap_mode, alpha, b.y, b.tx, nf, S, max_iterations, k_info, b.n_hat, b.word,
+                           b.synd, b.llr, llr_dtype, b.success, b.iters, b.post, post_dtype,
+                           h_bit_errors ? b.errors : nullptr, st);
+        if (rc) return rc;
         QR_CUDA_CHECK(cudaEventRecord(d->ev_compute[s], st));
         // stage 3: results of chunk c
         QR_CUDA_CHECK(cudaStreamWaitEvent(d->s_out, d->ev_compute[s], 0));

@@ -26,9 +26,30 @@ class Reconciler:
         self.N, self.C = dec.vnum, dec.cnum
         self.S = self.N // nm.bit_per_symbol
 
-    def run_device(self, y, x, max_iterations, k_info=None, want_post=True):
+    def run_device(self, y, x, max_iterations, k_info=None, want_post=True, stagewise=False):
         """y [B, S] float64 and x [B, S] int64 already on the GPU.  Returns a dict of CUDA tensors:
-        success, iters, post (or None), word, synd, bit_errors (int32 per frame over the first k_info bits)."""
+        success, iters, post (or None), word, synd, bit_errors (int32 per frame over the first k_info bits).
+
+        Default: ONE call into the library (qr_reconcile_device), intermediates in library-owned scratch.
+        stagewise=True runs the stages one library call at a time (same results; also returns the LLRs)."""
+        if not stagewise:
+            y = to_dev(y, torch.float64); x = to_dev(x, torch.int64)
+            B = y.shape[0]
+            dev = y.device
+            ok = torch.empty(B, dtype=torch.uint8, device=dev); it = torch.empty(B, dtype=torch.int32, device=dev)
+            post = torch.empty((B, self.N), dtype=self.llr_dtype, device=dev) if (want_post or k_info is not None) else None
+            word = torch.empty((B, self.N), dtype=torch.uint8, device=dev)
+            synd = torch.empty((B, self.C), dtype=torch.uint8, device=dev)
+            errs = torch.empty(B, dtype=torch.int32, device=dev) if k_info is not None else None
+            h = self.dec._handle(self.prec_code, self.lanes, self.schedule)
+            _abi.check(_abi.lib().qr_reconcile_device(
+                h, self.nm._h, self.mode, self.demap_code, self.alpha, y.data_ptr(), x.data_ptr(), B,
+                int(max_iterations), int(k_info if k_info is not None else 0), ok.data_ptr(), it.data_ptr(),
+                post.data_ptr() if post is not None else None,
+                _abi.QR_F32 if self.llr_dtype == torch.float32 else _abi.QR_F64, word.data_ptr(), synd.data_ptr(),
+                errs.data_ptr() if errs is not None else None, stream()))
+            return dict(success=ok, iters=it, post=post if want_post else None, word=word, synd=synd,
+                        bit_errors=errs, llr=None)
         from . import utils
         nm, dec = self.nm, self.dec
         B = y.shape[0]

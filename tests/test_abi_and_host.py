@@ -75,7 +75,8 @@ def test_product_never_touches_the_oracle():
         if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
             text = open(path).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
-            assert "libqroracle" not in text and "qr_oracle" not in text and "_ref" not in text.replace("_refresh", ""), path
+            assert "libqroracle" not in text and "qr_oracle" not in text and "oracle/_ref" not in text \
+                and "_ref/" not in text and "libqremu" not in text, path
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "mapper_*_snr2.npz"))))

@@ -129,3 +129,27 @@ def test_driver_semantics_and_modes(setup, monkeypatch):
     r = simulate_softening_snr_dB(9.0, s["qr"].Decoder(hv, hc), s["qr"].Matrix(hv, hc), pa1,
                                   np.array([0, 1], dtype=np.uint8), 20, 200, 1000)
     assert r[2] < 0.2
+
+
+@pytest.mark.parametrize("precision,demap", [("fp64", "exact"), ("fp32", "fast")])
+def test_single_call_chain_equals_stagewise(setup, precision, demap):
+    """qr_reconcile_device (whole chain in one library call) == the stages run one library call at a time
+    (more frames than lanes, frames finishing at different iterations)."""
+    s = setup
+    from qamreconciliation.pipeline import Reconciler
+    rng = np.random.default_rng(77)
+    pa = s["pa"]
+    frames = 300
+    snr = 4.4
+    n0 = pa.variance * 10 ** (-snr / 10) / 2
+    x = torch.tensor(rng.integers(0, 4, size=(frames, 324)), device="cuda")
+    y = torch.tensor(pa.constellation, device="cuda")[x] + np.sqrt(n0) * torch.tensor(rng.normal(size=(frames, 324)), device="cuda")
+    nm = s["qr"].NoiseMapper(pa, n0, s["cfg"])
+    for lanes in (32, 96):
+        rec = Reconciler(s["dec"], nm, precision=precision, demap=demap, lanes=lanes)
+        a = rec.run_device(y, x, 50, k_info=324)
+        b = rec.run_device(y, x, 50, k_info=324, stagewise=True)
+        for k in ("success", "iters", "word", "synd", "bit_errors"):
+            assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a["post"].view(torch.uint8), b["post"].view(torch.uint8))
+        assert 0 < int(a["success"].sum()) < frames
