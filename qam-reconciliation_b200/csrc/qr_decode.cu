@@ -52,6 +52,7 @@ __device__ __forceinline__ void check_phase(const DecodeParams<T> &P, int cur, c
     for (int32_t xt = bxid; xt < tl.nxt; xt += gx) {
         const int32_t jv = xt * tl.bx + tx;
         const LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
+        if (blockIdx.x == 0 && threadIdx.x == 0) P.ctrl[CTRL_REFILL_CNT + (cur ^ 1)] = 0;   // list the variable phase fills
         uint32_t bad = 0;
         if (L.active) {
             const int32_t first = byid * tl.by + ty, stride = gy * tl.by;
@@ -90,7 +91,7 @@ __device__ __forceinline__ void check_phase(const DecodeParams<T> &P, int cur, c
 }
 
 template <typename T, int VEC>
-__device__ __forceinline__ void var_phase(const DecodeParams<T> &P, int cur, const Tiling tl)
+__device__ __forceinline__ void var_phase(const DecodeParams<T> &P, int cur, int32_t step, const Tiling tl)
 {
     const int32_t tx = threadIdx.x % tl.bx, ty = threadIdx.x / tl.bx;
     const int32_t G = gridDim.x;
@@ -102,7 +103,7 @@ __device__ __forceinline__ void var_phase(const DecodeParams<T> &P, int cur, con
         LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
         decide_lanes<T, VEC>(P, cur, L);
         run_var_range<T, VEC>(P, L, byid * tl.by + ty, gy * tl.by, (int32_t)P.N);
-        if (byid == 0 && ty == 0) bookkeep_lanes<T, VEC>(P, cur, L);
+        if (byid == 0 && ty == 0) bookkeep_lanes<T, VEC>(P, cur, step, L);
     }
 }
 
@@ -123,6 +124,7 @@ __device__ __forceinline__ void check_phase_dyn(const DecodeParams<T> &P, int cu
         const int32_t jv = xt * tl.bx + tx;
         const LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
         if (byid == 0 && threadIdx.x == 0) P.work[kMaxLaneTiles + xt] = 0;   // variable-phase counter of this step
+        if (blockIdx.x == 0 && threadIdx.x == 0) P.ctrl[CTRL_REFILL_CNT + (cur ^ 1)] = 0;   // list the variable phase fills
         uint32_t bad = 0;
         for (;;) {
             __syncthreads();
@@ -169,7 +171,8 @@ __device__ __forceinline__ void check_phase_dyn(const DecodeParams<T> &P, int cu
 }
 
 template <typename T, int VEC>
-__device__ __forceinline__ void var_phase_dyn(const DecodeParams<T> &P, int cur, const Tiling tl, int32_t *s_base)
+__device__ __forceinline__ void var_phase_dyn(const DecodeParams<T> &P, int cur, int32_t step, const Tiling tl,
+                                              int32_t *s_base)
 {
     const int32_t tx = threadIdx.x % tl.bx, ty = threadIdx.x / tl.bx;
     const int32_t G = gridDim.x;
@@ -189,7 +192,89 @@ __device__ __forceinline__ void var_phase_dyn(const DecodeParams<T> &P, int cur,
             if (n0 >= N) break;
             run_var_range<T, VEC>(P, L, n0 + ty, tl.by, min(n0 + claim, N));
         }
-        if (byid == 0 && ty == 0) bookkeep_lanes<T, VEC>(P, cur, L);
+        if (byid == 0 && ty == 0) bookkeep_lanes<T, VEC>(P, cur, step, L);
+    }
+}
+
+// REFILL PHASE: ship finished frames' posterior columns, load newly assigned frames' LLR and syndrome
+// columns.  `buf` = the state buffer (and refill list) the variable phase of this step wrote.
+// Work item = (listed lane, block of kBlock*kRefillRows rows); a thread moves kRefillRows rows with all its
+// loads issued before the stores (the column side of every access is one 32-byte sector per element, the
+// caller's rows are contiguous across the threads of a warp).
+constexpr int kRefillRows = 8;
+
+template <typename T>
+__device__ __forceinline__ void refill_phase(const DecodeParams<T> &P, int buf)
+{
+    const int32_t cnt = ld_stream(&P.ctrl[CTRL_REFILL_CNT + buf]);
+    const int32_t span = kBlock * kRefillRows;
+    const int32_t vitems = (int32_t)((P.N + span - 1) / span), citems = (int32_t)((P.C + span - 1) / span);
+    const int64_t total = (int64_t)cnt * (vitems + citems);
+    const int32_t lanes = P.lanes;
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+        // row-block-major order: CTAs resident at the same time serve the SAME rows of neighbouring listed lanes,
+        // so when whole 8-lane sectors refill together (frames finishing in lock step) the sector traffic of the
+        // lane-interleaved rows is shared through L2 instead of being paid once per lane
+        const int32_t e = (int32_t)(item % cnt), r = (int32_t)(item / cnt);
+        const int32_t lane = ld_stream(&P.refill_list[(int64_t)buf * lanes + e]);
+        const LaneState s = ld_stream(&P.st[buf][lane]);
+        if (r >= vitems) {
+            if (s.frame >= 0 && s.fresh) {
+                const int32_t c0 = (r - vitems) * span + threadIdx.x;
+                uint8_t sy[kRefillRows];
+#pragma unroll
+                for (int i = 0; i < kRefillRows; ++i) {
+                    const int32_t ci = c0 + i * kBlock;
+                    if (ci < P.C) sy[i] = P.synd_in[(int64_t)s.frame * P.C + P.chk_order[ci]];
+                }
+#pragma unroll
+                for (int i = 0; i < kRefillRows; ++i) {
+                    const int32_t ci = c0 + i * kBlock;
+                    if (ci < P.C) P.synd[(int64_t)ci * lanes + lane] = sy[i];
+                }
+            }
+            continue;
+        }
+        const int32_t n0 = r * span + threadIdx.x;
+        if (s.retire >= 0 && P.post_out) {
+            if (ld_stream(&P.iters[s.retire]) == 0) {
+                // frames that never iterated: rare, element-wise path (input copy / input + 0.0 semantics)
+                LaneState only_retire = s;
+                only_retire.frame = -1;
+                for (int i = 0; i < kRefillRows; ++i) {
+                    const int32_t n = n0 + i * kBlock;
+                    if (n < P.N) refill_var_elem<T>(P, only_retire, lane, n);
+                }
+            } else {
+                T v[kRefillRows];
+#pragma unroll
+                for (int i = 0; i < kRefillRows; ++i) {
+                    const int32_t n = n0 + i * kBlock;
+                    if (n < P.N) v[i] = ld_stream(&P.post[(int64_t)n * lanes + lane]);
+                }
+#pragma unroll
+                for (int i = 0; i < kRefillRows; ++i) {
+                    const int32_t n = n0 + i * kBlock;
+                    if (n < P.N) store_output_llr(P.post_out, P.post_out_f64, (int64_t)s.retire * P.N + n, (double)v[i]);
+                }
+            }
+        }
+        if (s.frame >= 0 && s.fresh) {
+            T v[kRefillRows];
+#pragma unroll
+            for (int i = 0; i < kRefillRows; ++i) {
+                const int32_t n = n0 + i * kBlock;
+                if (n < P.N) v[i] = load_input_llr<T>(P.llr_in, P.llr_in_f64, (int64_t)s.frame * P.N + n);
+            }
+#pragma unroll
+            for (int i = 0; i < kRefillRows; ++i) {
+                const int32_t n = n0 + i * kBlock;
+                if (n < P.N) {
+                    P.llr[(int64_t)n * lanes + lane] = v[i];
+                    P.post[(int64_t)n * lanes + lane] = v[i];
+                }
+            }
+        }
     }
 }
 
@@ -210,8 +295,16 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kBlock, min_ctas<T, VEC>()) k_var(DecodeParams<T> P, int step, Tiling tl)
 {
     if (*(volatile int32_t *)&P.ctrl[CTRL_SNAPSHOT] == 0) return;
-    var_phase<T, VEC>(P, step & 1, tl);
+    var_phase<T, VEC>(P, step & 1, step, tl);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[1], 1ULL);
+}
+
+// step < 0: the initial load of the first generation of frames; otherwise only if a frame finished in `step`
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_refill(DecodeParams<T> P, int step)
+{
+    if (step >= 0 && *(volatile int32_t *)&P.ctrl[CTRL_FIN_STEP] != step) return;
+    refill_phase<T>(P, step < 0 ? 0 : (step & 1) ^ 1);
 }
 
 template <typename T, int VEC, int DSEL>
@@ -220,12 +313,18 @@ __global__ void __launch_bounds__(kBlock, min_ctas<T, VEC>()) k_persistent(Decod
     __shared__ int32_t s_flags[32 * VEC];
     __shared__ int32_t s_base;
     cg::grid_group grid = cg::this_grid();
+    refill_phase<T>(P, 0);      // first generation of frames into the lanes
+    grid.sync();
     for (int step = 0;; ++step) {
         check_phase_dyn<T, VEC, DSEL>(P, step & 1, tl, s_flags, &s_base);
         grid.sync();
-        var_phase_dyn<T, VEC>(P, step & 1, tl, &s_base);
+        var_phase_dyn<T, VEC>(P, step & 1, step, tl, &s_base);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[1], 1ULL);
         grid.sync();
+        if (*(volatile int32_t *)&P.ctrl[CTRL_FIN_STEP] == step) {   // a frame finished: ship it, refill its lane
+            refill_phase<T>(P, (step & 1) ^ 1);
+            grid.sync();
+        }
         if (*(volatile int32_t *)&P.ctrl[CTRL_REMAINING] <= 0) break;
     }
 }
@@ -233,7 +332,7 @@ __global__ void __launch_bounds__(kBlock, min_ctas<T, VEC>()) k_persistent(Decod
 // lane l starts on frame l (if there is one); everything else is idle
 __global__ void k_init_batch(LaneState *st0, LaneState *st1, int32_t *unsat0, int32_t *unsat1,
                              int32_t lanes, int64_t frames, int32_t *ctrl, int32_t *work,
-                             unsigned long long *stats)
+                             unsigned long long *stats, int32_t *refill_list)
 {
     const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l < lanes) {
@@ -241,16 +340,20 @@ __global__ void k_init_batch(LaneState *st0, LaneState *st1, int32_t *unsat0, in
         s.frame = (int64_t)l < frames ? l : -1;
         s.iter = 0;
         s.fresh = s.frame >= 0;
-        s.pad = 0;
+        s.retire = -1;
         st0[l] = s;
         st1[l] = s;
         unsat0[l] = 0;
         unsat1[l] = 0;
+        if (s.frame >= 0) refill_list[l] = l;      // first generation: lanes 0 .. min(lanes, frames) - 1
     }
     for (int32_t i = l; i < 2 * kMaxLaneTiles; i += gridDim.x * blockDim.x) work[i] = 0;
     if (l == 0) {
         ctrl[CTRL_NEXT_FRAME] = (int32_t)min((int64_t)lanes, frames);
         ctrl[CTRL_REMAINING] = (int32_t)frames;
+        ctrl[CTRL_FIN_STEP] = -1;
+        ctrl[CTRL_REFILL_CNT + 0] = (int32_t)min((int64_t)lanes, frames);
+        ctrl[CTRL_REFILL_CNT + 1] = 0;
         stats[0] = 0;
         stats[1] = 0;
     }
@@ -296,7 +399,7 @@ static DecodeParams<T> make_params(const qr_decoder *d, const void *llr, int llr
     P.frames = frames; P.maxiter = maxiter;
     P.success = success; P.iters = iters;
     P.post_out = post; P.post_out_f64 = post_dtype == QR_F64;
-    P.ctrl = d->ctrl; P.stats = d->stats; P.work = d->work;
+    P.ctrl = d->ctrl; P.stats = d->stats; P.work = d->work; P.refill_list = d->refill_list;
     return P;
 }
 
@@ -341,10 +444,13 @@ static int run_batch_t(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t str
     const int64_t rounds = (P.frames + P.lanes - 1) / P.lanes;
     const int64_t max_steps = rounds * ((int64_t)P.maxiter + 2) + 2;
     const int chunk = P.maxiter + 1;   // a lane finishes a frame at least every maxiter + 1 steps
+    const int rgrid = 2 * d->sm_count;
+    k_refill<T><<<rgrid, kBlock, 0, stream>>>(P, -1);
     for (int64_t step = 0; step < max_steps;) {
         for (int k = 0; k < chunk && step < max_steps; ++k, ++step) {
-            k_check<T, VEC, DSEL><<<grid, kBlock, 0, stream>>>(P, (int)(step & 1), tl);
-            k_var<T, VEC><<<grid, kBlock, 0, stream>>>(P, (int)(step & 1), tl);
+            k_check<T, VEC, DSEL><<<grid, kBlock, 0, stream>>>(P, (int)step, tl);
+            k_var<T, VEC><<<grid, kBlock, 0, stream>>>(P, (int)step, tl);
+            k_refill<T><<<rgrid, kBlock, 0, stream>>>(P, (int)step);
         }
         QR_CUDA_CHECK(cudaGetLastError());
         QR_CUDA_CHECK(cudaMemcpyAsync(d->h_ctrl, d->ctrl, CTRL_WORDS * sizeof(int32_t),
@@ -418,6 +524,7 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
         QR_CUDA_CHECK(cudaMalloc((void **)&d->ctrl, qr::CTRL_WORDS * sizeof(int32_t)));
         QR_CUDA_CHECK(cudaMalloc((void **)&d->stats, 2 * sizeof(unsigned long long)));
         QR_CUDA_CHECK(cudaMalloc((void **)&d->work, 2 * qr::kMaxLaneTiles * sizeof(int32_t)));
+        QR_CUDA_CHECK(cudaMalloc((void **)&d->refill_list, 2 * L * sizeof(int32_t)));
         QR_CUDA_CHECK(cudaMemset(d->c2v, 0, (size_t)g->E * L * w));
         QR_CUDA_CHECK(cudaMemset(d->post, 0, (size_t)g->N * L * w));
         QR_CUDA_CHECK(cudaMemset(d->llr, 0, (size_t)g->N * L * w));
@@ -442,7 +549,7 @@ void qr_decoder_destroy(qr_decoder *d)
     cudaGetDevice(&prev);
     cudaSetDevice(d->device);
     cudaFree(d->c2v); cudaFree(d->post); cudaFree(d->llr); cudaFree(d->synd);
-    cudaFree(d->st); cudaFree(d->unsat); cudaFree(d->ctrl); cudaFree(d->stats); cudaFree(d->work);
+    cudaFree(d->st); cudaFree(d->unsat); cudaFree(d->ctrl); cudaFree(d->stats); cudaFree(d->work); cudaFree(d->refill_list);
     cudaFree(d->pipe_buf);
     cudaFree(d->dev_buf);
     if (d->pipe_streams_ready) {
@@ -484,7 +591,7 @@ int qr_decode_batch(qr_decoder *d, const void *d_llr, int llr_dtype, const uint8
         QR_CUDA_CHECK(cudaSetDevice(d->device));
         const int32_t lanes = (int32_t)std::min<int64_t>(d->lanes, (frames + 31) / 32 * 32);
         qr::k_init_batch<<<(lanes + 255) / 256, 256, 0, stream>>>(
-            d->st, d->st + lanes, d->unsat, d->unsat + lanes, lanes, frames, d->ctrl, d->work, d->stats);
+            d->st, d->st + lanes, d->unsat, d->unsat + lanes, lanes, frames, d->ctrl, d->work, d->stats, d->refill_list);
         QR_CUDA_CHECK(cudaGetLastError());
         d->last_stream = stream;
         if (d->precision == QR_F64) {

@@ -16,16 +16,22 @@
 //
 // A lane runs one frame at a time.  State per lane (double-buffered by step parity, because the
 // variable phase reads the old state while one thread per lane writes the new one):
-//   frame  frame id (-1: idle)      iter  completed variable updates      fresh  1 until the lane's
-//   columns of llr/post/synd have been loaded (while fresh: c2v == 0, post == llr == input row).
-// One schedule step = check phase then variable phase:
+//   frame  frame id (-1: idle)      iter  completed variable updates
+//   fresh  1 until the first variable update of the frame (the lane's c2v column still holds the
+//          previous frame's messages and counts as zero)
+//   retire frame id whose posteriors still have to be written out of the lane's column (-1: none)
+// One schedule step = check phase, variable phase and -- only when a frame finished -- a refill phase:
 //   check phase, lane at iteration t: tests the syndrome on post_t (decoder.pyx:235-257) and
 //       computes c2v_{t+1} from v2c_t = post_t - c2v_t (decoder.pyx:322-369).
 //   variable phase: if the syndrome test passed -> frame done, (success=1, iters=t, post_t)
 //       (decoder.pyx:402-405 for t=0, :431-433 for t>0); else if t == max_iterations -> done,
 //       (0, max_iterations, post_t) (:435-436); else post_{t+1} = llr + sum c2v_{t+1}
-//       (decoder.pyx:291-293).  A finished lane writes its posteriors out and takes the next
-//       frame of the batch (continuous batching; no message columns are ever moved).
+//       (decoder.pyx:291-293).  A finished lane is handed the next frame of the batch at once.
+//   refill phase: finished lanes' posterior columns go to the caller's rows, newly assigned frames'
+//       LLR / syndrome rows come into the lane's columns (post = llr).  Message columns are never
+//       moved or zeroed: converged frames are compacted out by refilling their lane (continuous
+//       batching).  Check and variable phases therefore only ever touch the lane-interleaved arrays
+//       and run ONE code path whatever the mix of fresh, running and finishing lanes in a thread.
 //
 // Everything here is __host__ __device__ so tests/emu can run the same code on the CPU.
 #pragma once
@@ -42,10 +48,13 @@ struct LaneState {
     int32_t frame;
     int32_t iter;
     int32_t fresh;
-    int32_t pad;
+    int32_t retire;
 };
 
-enum : int { CTRL_NEXT_FRAME = 0, CTRL_REMAINING = 1, CTRL_SNAPSHOT = 2, CTRL_WORDS = 8 };
+// CTRL_FIN_STEP: index of the last step in which a frame finished (so a refill phase is due)
+// CTRL_REFILL_CNT[2]: lanes listed for the refill phase, double-buffered like the lane state
+enum : int { CTRL_NEXT_FRAME = 0, CTRL_REMAINING = 1, CTRL_SNAPSHOT = 2, CTRL_FIN_STEP = 3, CTRL_REFILL_CNT = 4,
+             CTRL_WORDS = 8 };
 constexpr int kMaxLaneTiles = 1 << 15;
 
 template <typename T>
@@ -75,6 +84,7 @@ struct DecodeParams {
     // control words and counters
     int32_t *ctrl;
     int32_t *work;              // [2][kMaxLaneTiles] row counters of the persistent kernel's work stealing
+    int32_t *refill_list;       // [2][lanes] lanes the refill phase has to serve (null: scan all lanes)
     unsigned long long *stats;  // [0] flooding iterations summed over finished frames
 };
 
@@ -319,7 +329,7 @@ struct LaneInfo {
     int32_t frame[VEC];
     int32_t iter[VEC];
     uint32_t active;  // bit k: lane runs a frame
-    uint32_t fresh;   // bit k: lane's columns are not loaded yet
+    uint32_t fresh;   // bit k: no variable update yet for this frame: its c2v column counts as zero
     // variable phase decisions
     uint32_t fin_ok, fin_fail, upd;
 };
@@ -355,55 +365,42 @@ QR_HD void decide_lanes(const DecodeParams<T> &P, int cur, LaneInfo<VEC> &L)
     }
 }
 
+template <int D>
+QR_HD void load_index_row(const int32_t *__restrict__ tab, int32_t first, int32_t (&v)[D])
+{
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = tab[first + i];
+}
+
 // ---------------------------------------------------------------------------------------------
-// CHECK PHASE item: internal check `ci` (degree deg, first CSR slot slot0) for the thread's lanes.
-// Returns a bit per lane: 1 = this check is NOT satisfied by the lane's current posteriors.
+// CHECK PHASE item: internal check `ci` (first CSR slot slot0) for the thread's lanes, given the
+// variable ids of its edges.  All 2*deg 128-bit row loads are issued back to back before anything
+// consumes them.  Returns a bit per lane: 1 = this check is NOT satisfied by the lane's posteriors.
 // D > 0: compile-time degree (registers); D == 0: run-time degree <= kMaxCheckDegree.
 template <typename T, int VEC, int D>
 QR_HD uint32_t check_item(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t ci, int32_t slot0,
-                          int32_t deg_rt)
+                          int32_t deg_rt, const int32_t *v)
 {
     constexpr int CAP = D > 0 ? D : kMaxCheckDegree;
     constexpr int UNR = D > 0 ? D : 1;  // full unroll for compile-time degrees, none otherwise
     const int deg = D > 0 ? D : deg_rt;
     const int32_t lanes = P.lanes;
-    Vec<T, VEC> x[CAP];  // per edge: v2c in, c2v out
-    uint32_t par = 0;    // bit k: parity of negative posteriors XOR syndrome
-    uint8_t sy[VEC];
-    {
-        const uint8_t *row = P.synd + (int64_t)ci * lanes + L.l0;
+    Vec<T, VEC> pv[CAP], x[CAP];
+#pragma unroll UNR
+    for (int i = 0; i < deg; ++i) pv[i] = ld_row<T, VEC>(P.post, D > 0 ? v[i] : P.slot_var[slot0 + i], lanes, L.l0);
+#pragma unroll UNR
+    for (int i = 0; i < deg; ++i) x[i] = ld_row<T, VEC>(P.c2v, slot0 + i, lanes, L.l0);
+    const Vec<uint8_t, VEC> sy = *reinterpret_cast<const Vec<uint8_t, VEC> *>(P.synd + (int64_t)ci * lanes + L.l0);
+    uint32_t par = 0;   // bit k: syndrome XOR parity of the negative posteriors
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) sy[k] = row[k];
-    }
-    if (L.fresh) {
-        const int32_t c_orig = P.chk_order[ci];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k)
-            if (L.fresh >> k & 1) {
-                sy[k] = P.synd_in[(int64_t)L.frame[k] * P.C + c_orig];
-                P.synd[(int64_t)ci * lanes + L.l0 + k] = sy[k];
-            }
-    }
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) par |= (uint32_t)(sy[k] & 1u) << k;
-
+    for (int k = 0; k < VEC; ++k) par |= (uint32_t)(sy.v[k] & 1u) << k;
 #pragma unroll UNR
     for (int i = 0; i < deg; ++i) {
-        const int32_t v = P.slot_var[slot0 + i];
-        Vec<T, VEC> pv = ld_row<T, VEC>(P.post, v, lanes, L.l0);
-        Vec<T, VEC> cv = ld_row<T, VEC>(P.c2v, slot0 + i, lanes, L.l0);
-        if (L.fresh) {
-#pragma unroll
-            for (int k = 0; k < VEC; ++k)
-                if (L.fresh >> k & 1) {
-                    pv.v[k] = load_input_llr<T>(P.llr_in, P.llr_in_f64, (int64_t)L.frame[k] * P.N + v);
-                    cv.v[k] = (T)0;
-                }
-        }
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            par ^= (uint32_t)(pv.v[k] < (T)0) << k;      // decoder.pyx:244 (strict <)
-            x[i].v[k] = pv.v[k] - cv.v[k];               // decoder.pyx:295-297
+            par ^= (uint32_t)(pv[i].v[k] < (T)0) << k;                      // decoder.pyx:244 (strict <)
+            const T old = (L.fresh >> k & 1) ? (T)0 : x[i].v[k];            // first half-iteration: c2v == 0 (:408)
+            x[i].v[k] = pv[i].v[k] - old;                                   // decoder.pyx:295-297
         }
     }
     // node update, one lane at a time (keeps only one lane's scratch live)
@@ -412,7 +409,7 @@ QR_HD uint32_t check_item(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int3
         T xs[CAP];
 #pragma unroll UNR
         for (int i = 0; i < deg; ++i) xs[i] = x[i].v[k];
-        MathOf<T>::template run<CAP, UNR>(deg, xs, (sy[k] & 1u) != 0);
+        MathOf<T>::template run<CAP, UNR>(deg, xs, (sy.v[k] & 1u) != 0);
 #pragma unroll UNR
         for (int i = 0; i < deg; ++i) x[i].v[k] = xs[i];
     }
@@ -425,63 +422,124 @@ QR_HD uint32_t check_item(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int3
 // (decoder.pyx:243-249); for the 0/1 bytes every caller passes that is the low bit, which is
 // what the kernels use.
 
+// All checks k = first, first+stride, ... of one degree bin, for the thread's lanes.  The index row of
+// the NEXT check is fetched while the current one computes.
+template <typename T, int VEC, int D>
+QR_HD uint32_t run_check_bin(const DecodeParams<T> &P, const LaneInfo<VEC> &L, const CheckBin &bin,
+                             int32_t first, int32_t stride)
+{
+    uint32_t bad = 0;
+    if constexpr (D > 0) {
+        int32_t cur[D], nxt[D];
+        if (first < bin.count) load_index_row<D>(P.slot_var, bin.slot_begin + first * D, cur);
+        for (int32_t k = first; k < bin.count; k += stride) {
+            const int32_t kn = k + stride;
+            if (kn < bin.count) load_index_row<D>(P.slot_var, bin.slot_begin + kn * D, nxt);
+            bad |= check_item<T, VEC, D>(P, L, bin.chk_begin + k, bin.slot_begin + k * D, D, cur);
+#pragma unroll
+            for (int i = 0; i < D; ++i) cur[i] = nxt[i];
+        }
+    } else {
+        for (int32_t k = first; k < bin.count; k += stride)
+            bad |= check_item<T, VEC, 0>(P, L, bin.chk_begin + k, bin.slot_begin + k * bin.degree, bin.degree,
+                                         nullptr);
+    }
+    return bad;
+}
+
 // ---------------------------------------------------------------------------------------------
-// VARIABLE PHASE item: variable n for the thread's lanes (decisions already in L).
+// VARIABLE PHASE.  post_{t+1}[n] = llr[n] + sum of c2v over the variable's edges in ascending edge id
+// (decoder.pyx:291-293) for the lanes that iterate on; lanes that just finished keep post_t (the refill
+// phase ships it), idle lanes are don't-care.  MASKED = some lane of the vector does not update.
+template <typename T, int VEC, int DV>
+QR_HD void var_item_fixed(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t n, const int32_t (&slot)[DV],
+                          bool masked)
+{
+    const int32_t lanes = P.lanes;
+    Vec<T, VEC> acc = ld_row<T, VEC>(P.llr, n, lanes, L.l0);
+    Vec<T, VEC> m[DV], old;
+#pragma unroll
+    for (int i = 0; i < DV; ++i) m[i] = ld_row<T, VEC>(P.c2v, slot[i], lanes, L.l0);
+    if (masked) old = ld_row<T, VEC>(P.post, n, lanes, L.l0);
+#pragma unroll
+    for (int i = 0; i < DV; ++i) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc.v[k] = acc.v[k] + m[i].v[k];
+    }
+    if (masked) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+            if (!(L.upd >> k & 1)) acc.v[k] = old.v[k];
+    }
+    st_row<T, VEC>(P.post, n, lanes, L.l0, acc);
+}
+
+// any variable degree (run-time loop over the variable's slot list)
 template <typename T, int VEC>
 QR_HD void var_item(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t n)
 {
     const int32_t lanes = P.lanes;
-    const uint32_t fin = L.fin_ok | L.fin_fail;
-    if (fin) {
-        // finished lanes: the posteriors of the iteration that ended the frame go to the caller
-        Vec<T, VEC> old_post;
-        if (fin & ~L.fresh) old_post = ld_row<T, VEC>(P.post, n, lanes, L.l0);
-        if (P.post_out) {
+    Vec<T, VEC> acc = ld_row<T, VEC>(P.llr, n, lanes, L.l0);
+    const bool masked = L.upd != (1u << VEC) - 1u;
+    Vec<T, VEC> old;
+    if (masked) old = ld_row<T, VEC>(P.post, n, lanes, L.l0);
+    const int32_t q0 = P.var_ptr[n], q1 = P.var_ptr[n + 1];
+    for (int32_t q = q0; q < q1; ++q) {
+        const Vec<T, VEC> m = ld_row<T, VEC>(P.c2v, P.var_slot[q], lanes, L.l0);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k)
-                if (fin >> k & 1) {
-                    const int64_t idx = (int64_t)L.frame[k] * P.N + n;
-                    if (L.fresh >> k & 1) {
-                        // A frame that never iterated.  Input already consistent: the reference copies
-                        // it (decoder.pyx:404), bit for bit when both sides are fp64.  max_iterations
-                        // == 0: the reference still ran its first variable pass with c2v == 0
-                        // (decoder.pyx:420-421), i.e. llr + 0.0 per edge, which turns -0.0 into +0.0.
-                        const bool copied = (L.fin_ok >> k & 1) != 0;
-                        if (copied && P.llr_in_f64 && P.post_out_f64) {
-                            static_cast<double *>(P.post_out)[idx] = static_cast<const double *>(P.llr_in)[idx];
-                        } else {
-                            double val = (double)load_input_llr<T>(P.llr_in, P.llr_in_f64, idx);
-                            if (!copied && P.var_ptr[n + 1] > P.var_ptr[n]) val = val + 0.0;
-                            store_output_llr(P.post_out, P.post_out_f64, idx, val);
-                        }
-                    } else {
-                        store_output_llr(P.post_out, P.post_out_f64, idx, (double)old_post.v[k]);
-                    }
-                }
-        }
+        for (int k = 0; k < VEC; ++k) acc.v[k] = acc.v[k] + m.v[k];
     }
-    if (L.upd) {
-        Vec<T, VEC> acc = ld_row<T, VEC>(P.llr, n, lanes, L.l0);
-        if (L.fresh & L.upd) {
+    if (masked) {
 #pragma unroll
-            for (int k = 0; k < VEC; ++k)
-                if ((L.fresh & L.upd) >> k & 1)
-                    acc.v[k] = load_input_llr<T>(P.llr_in, P.llr_in_f64, (int64_t)L.frame[k] * P.N + n);
-            st_row<T, VEC>(P.llr, n, lanes, L.l0, acc);  // the other lanes rewrite their own value
-        }
-        const int32_t q0 = P.var_ptr[n], q1 = P.var_ptr[n + 1];
-        for (int32_t q = q0; q < q1; ++q) {               // ascending edge id: decoder.pyx:291-293
-            Vec<T, VEC> m = ld_row<T, VEC>(P.c2v, P.var_slot[q], lanes, L.l0);
+        for (int k = 0; k < VEC; ++k)
+            if (!(L.upd >> k & 1)) acc.v[k] = old.v[k];
+    }
+    st_row<T, VEC>(P.post, n, lanes, L.l0, acc);
+}
+
+template <typename T, int VEC, int DV, int U>
+QR_HD void run_var_fixed(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t first, int32_t stride,
+                         int32_t n_end, bool masked)
+{
+    // U variables per trip (n, n+stride, ...): U*(DV+1) independent row loads in flight per thread;
+    // the slot rows of the next trip are fetched while this one is summed.
+    const int32_t N = n_end;
+    int32_t cur[U][DV], nxt[U][DV];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) acc.v[k] = acc.v[k] + m.v[k];
+    for (int u = 0; u < U; ++u)
+        if (first + u * stride < N) load_index_row<DV>(P.var_slot, (first + u * stride) * DV, cur[u]);
+    for (int32_t n = first; n < N; n += U * stride) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int32_t nn = n + (U + u) * stride;
+            if (nn < N) load_index_row<DV>(P.var_slot, nn * DV, nxt[u]);
         }
-        // lanes that did not update (idle or just finished) receive junk: nothing reads their
-        // posterior column again before a new frame overwrites it
-        st_row<T, VEC>(P.post, n, lanes, L.l0, acc);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (n + u * stride < N) var_item_fixed<T, VEC, DV>(P, L, n + u * stride, cur[u], masked);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int i = 0; i < DV; ++i) cur[u][i] = nxt[u][i];
     }
 }
 
-// One thread per lane-vector (the one that owns variable 0) advances the lane state machine.
+// All variables n = first, first+stride, ... < n_end for the thread's lanes (decisions already in L).
+template <typename T, int VEC>
+QR_HD void run_var_range(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t first, int32_t stride,
+                         int32_t n_end)
+{
+    if (!L.upd) return;
+    constexpr int U = 2;  // 4 was measured slower on B200 (register spills in the persistent kernel)
+    // the common regular degree gets an unrolled, index-prefetching loop; anything else the generic one
+    if (P.var_deg == 3) {
+        run_var_fixed<T, VEC, 3, U>(P, L, first, stride, n_end, L.upd != (1u << VEC) - 1u);
+        return;
+    }
+    for (int32_t n = first; n < n_end; n += stride) var_item<T, VEC>(P, L, n);
+}
+
+// One thread per lane-vector advances the lane state machine, once per step.
 #if defined(__CUDA_ARCH__)
 #define QR_ATOMIC_ADD_I32(p, v) atomicAdd((p), (v))
 #define QR_ATOMIC_ADD_U64(p, v) atomicAdd((p), (v))
@@ -491,7 +549,7 @@ QR_HD void var_item(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t n)
 #endif
 
 template <typename T, int VEC>
-QR_HD void bookkeep_lanes(const DecodeParams<T> &P, int cur, const LaneInfo<VEC> &L)
+QR_HD void bookkeep_lanes(const DecodeParams<T> &P, int cur, int32_t step, const LaneInfo<VEC> &L)
 {
     const int nxt = cur ^ 1;
 #pragma unroll
@@ -501,14 +559,20 @@ QR_HD void bookkeep_lanes(const DecodeParams<T> &P, int cur, const LaneInfo<VEC>
         s.frame = L.frame[k];
         s.iter = L.iter[k];
         s.fresh = (L.fresh >> k) & 1;
-        s.pad = 0;
+        s.retire = -1;
         if ((L.fin_ok | L.fin_fail) >> k & 1) {
             const bool ok = (L.fin_ok >> k & 1) != 0;
             P.success[s.frame] = ok ? 1 : 0;
             P.iters[s.frame] = ok ? s.iter : P.maxiter;
             QR_ATOMIC_ADD_U64(&P.stats[0], (unsigned long long)s.iter);
             QR_ATOMIC_ADD_I32(&P.ctrl[CTRL_REMAINING], -1);
-            int32_t nf = QR_ATOMIC_ADD_I32(&P.ctrl[CTRL_NEXT_FRAME], 1);
+            s.retire = s.frame;                      // the refill phase ships this frame's posteriors
+            P.ctrl[CTRL_FIN_STEP] = step;            // ... and is due after this step
+            if (P.refill_list) {
+                const int32_t slot = QR_ATOMIC_ADD_I32(&P.ctrl[CTRL_REFILL_CNT + nxt], 1);
+                P.refill_list[(int64_t)nxt * P.lanes + slot] = lane;
+            }
+            const int32_t nf = QR_ATOMIC_ADD_I32(&P.ctrl[CTRL_NEXT_FRAME], 1);
             if ((int64_t)nf < P.frames) { s.frame = nf; s.iter = 0; s.fresh = 1; }
             else { s.frame = -1; s.iter = 0; s.fresh = 0; }
         } else if (L.upd >> k & 1) {
@@ -521,153 +585,45 @@ QR_HD void bookkeep_lanes(const DecodeParams<T> &P, int cur, const LaneInfo<VEC>
 }
 
 // ---------------------------------------------------------------------------------------------
-// FAST PATHS.  The per-item functions above are general (fresh lanes, run-time degrees); the hot
-// loops below cover the steady state -- no fresh lane in the thread's vector, compile-time check
-// degree, regular variable degree -- and are written for memory-level parallelism: the index row of
-// the NEXT item is fetched while the current one computes, and all 2*D (check) or DV+1 (variable)
-// 128-bit row loads of an item are issued back to back before anything consumes them.
-
-template <int D>
-QR_HD void load_index_row(const int32_t *__restrict__ tab, int32_t first, int32_t (&v)[D])
+// REFILL PHASE, one (lane, variable) element: ship the finished frame's posterior, bring in the new
+// frame's channel LLR.  `s` is the lane's state as the variable phase of this step left it.
+template <typename T>
+QR_HD void refill_var_elem(const DecodeParams<T> &P, const LaneState &s, int32_t lane, int32_t n)
 {
-#pragma unroll
-    for (int i = 0; i < D; ++i) v[i] = tab[first + i];
-}
-
-template <typename T, int VEC, int D>
-QR_HD uint32_t check_item_fast(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t ci, int32_t slot0,
-                               const int32_t (&v)[D])
-{
-    const int32_t lanes = P.lanes;
-    Vec<T, VEC> pv[D], x[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) pv[i] = ld_row<T, VEC>(P.post, v[i], lanes, L.l0);
-#pragma unroll
-    for (int i = 0; i < D; ++i) x[i] = ld_row<T, VEC>(P.c2v, slot0 + i, lanes, L.l0);
-    const Vec<uint8_t, VEC> sy = *reinterpret_cast<const Vec<uint8_t, VEC> *>(P.synd + (int64_t)ci * lanes + L.l0);
-    uint32_t par = 0;
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) par |= (uint32_t)(sy.v[k] & 1u) << k;
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            par ^= (uint32_t)(pv[i].v[k] < (T)0) << k;       // decoder.pyx:244 (strict <)
-            x[i].v[k] = pv[i].v[k] - x[i].v[k];               // decoder.pyx:295-297
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-        T xs[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) xs[i] = x[i].v[k];
-        MathOf<T>::template run<D, D>(D, xs, (sy.v[k] & 1u) != 0);
-#pragma unroll
-        for (int i = 0; i < D; ++i) x[i].v[k] = xs[i];
-    }
-#pragma unroll
-    for (int i = 0; i < D; ++i) st_row<T, VEC>(P.c2v, slot0 + i, lanes, L.l0, x[i]);
-    return par & L.active;
-}
-
-// All checks k = first, first+stride, ... of one degree bin, for the thread's lanes.
-template <typename T, int VEC, int D>
-QR_HD uint32_t run_check_bin(const DecodeParams<T> &P, const LaneInfo<VEC> &L, const CheckBin &bin,
-                             int32_t first, int32_t stride)
-{
-    uint32_t bad = 0;
-    if constexpr (D > 0) {
-        if (!L.fresh) {
-            int32_t cur[D], nxt[D];
-            if (first < bin.count) load_index_row<D>(P.slot_var, bin.slot_begin + first * D, cur);
-            for (int32_t k = first; k < bin.count; k += stride) {
-                const int32_t kn = k + stride;
-                if (kn < bin.count) load_index_row<D>(P.slot_var, bin.slot_begin + kn * D, nxt);
-                bad |= check_item_fast<T, VEC, D>(P, L, bin.chk_begin + k, bin.slot_begin + k * D, cur);
-#pragma unroll
-                for (int i = 0; i < D; ++i) cur[i] = nxt[i];
-            }
-            return bad;
-        }
-    }
-    for (int32_t k = first; k < bin.count; k += stride)
-        bad |= check_item<T, VEC, D>(P, L, bin.chk_begin + k, bin.slot_begin + k * bin.degree, bin.degree);
-    return bad;
-}
-
-template <typename T, int VEC, int DV>
-QR_HD void var_item_fast(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t n, const int32_t (&slot)[DV])
-{
-    const int32_t lanes = P.lanes;
-    Vec<T, VEC> acc = ld_row<T, VEC>(P.llr, n, lanes, L.l0);
-    Vec<T, VEC> m[DV];
-#pragma unroll
-    for (int i = 0; i < DV; ++i) m[i] = ld_row<T, VEC>(P.c2v, slot[i], lanes, L.l0);
-#pragma unroll
-    for (int i = 0; i < DV; ++i) {                        // ascending edge id: decoder.pyx:291-293
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] = acc.v[k] + m[i].v[k];
-    }
-    st_row<T, VEC>(P.post, n, lanes, L.l0, acc);
-}
-
-template <typename T, int VEC, int DV, int U>
-QR_HD void run_var_fast(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t first, int32_t stride,
-                        int32_t n_end)
-{
-    // U variables per trip (n, n+stride, ...): U*(DV+1) independent row loads in flight per thread;
-    // the slot rows of the next trip are fetched while this one is summed.
-    const int32_t N = n_end, lanes = P.lanes;
-    int32_t cur[U][DV], nxt[U][DV];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (first + u * stride < N) load_index_row<DV>(P.var_slot, (first + u * stride) * DV, cur[u]);
-    for (int32_t n = first; n < N; n += U * stride) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int32_t nn = n + (U + u) * stride;
-            if (nn < N) load_index_row<DV>(P.var_slot, nn * DV, nxt[u]);
-        }
-        if (n + (U - 1) * stride < N) {
-            Vec<T, VEC> acc[U], m[U][DV];
-#pragma unroll
-            for (int u = 0; u < U; ++u) acc[u] = ld_row<T, VEC>(P.llr, n + u * stride, lanes, L.l0);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int i = 0; i < DV; ++i) m[u][i] = ld_row<T, VEC>(P.c2v, cur[u][i], lanes, L.l0);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-#pragma unroll
-                for (int i = 0; i < DV; ++i)                  // ascending edge id: decoder.pyx:291-293
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) acc[u].v[k] = acc[u].v[k] + m[u][i].v[k];
-                st_row<T, VEC>(P.post, n + u * stride, lanes, L.l0, acc[u]);
+    const int64_t at = (int64_t)n * P.lanes + lane;
+    if (s.retire >= 0 && P.post_out) {
+        const int64_t idx = (int64_t)s.retire * P.N + n;
+        if (ld_stream(&P.iters[s.retire]) == 0) {   // (L2 loads: written by another SM in the phase before)
+            // A frame that never iterated.  Input already consistent: the reference copies it
+            // (decoder.pyx:404), bit for bit when both sides are fp64.  max_iterations == 0: the
+            // reference still ran its first variable pass with c2v == 0 (decoder.pyx:420-421), i.e.
+            // llr + 0.0 per edge, which turns -0.0 into +0.0.
+            const bool copied = *static_cast<const volatile uint8_t *>(&P.success[s.retire]) != 0;
+            if (copied && P.llr_in_f64 && P.post_out_f64) {
+                static_cast<double *>(P.post_out)[idx] = static_cast<const double *>(P.llr_in)[idx];
+            } else {
+                double val = (double)load_input_llr<T>(P.llr_in, P.llr_in_f64, idx);
+                if (!copied && P.var_ptr[n + 1] > P.var_ptr[n]) val = val + 0.0;
+                store_output_llr(P.post_out, P.post_out_f64, idx, val);
             }
         } else {
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (n + u * stride < N) var_item_fast<T, VEC, DV>(P, L, n + u * stride, cur[u]);
+            store_output_llr(P.post_out, P.post_out_f64, idx, (double)ld_stream(&P.post[at]));
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int i = 0; i < DV; ++i) cur[u][i] = nxt[u][i];
+    }
+    if (s.frame >= 0 && s.fresh) {
+        const T v = load_input_llr<T>(P.llr_in, P.llr_in_f64, (int64_t)s.frame * P.N + n);
+        P.llr[at] = v;
+        P.post[at] = v;
     }
 }
 
-// All variables n = first, first+stride, ... for the thread's lanes (decisions already in L).
-template <typename T, int VEC>
-QR_HD void run_var_range(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t first, int32_t stride,
-                         int32_t n_end)
+template <typename T>
+QR_HD void refill_chk_elem(const DecodeParams<T> &P, const LaneState &s, int32_t lane, int32_t ci)
 {
-    if (!(L.upd | L.fin_ok | L.fin_fail)) return;
-    const bool steady = !L.fresh && !(L.fin_ok | L.fin_fail) && L.upd == L.active;
-    constexpr int U = 2;  // 4 was measured slower on B200 (register spills in the persistent kernel)
-    if (steady && P.var_deg == 3) { run_var_fast<T, VEC, 3, U>(P, L, first, stride, n_end); return; }
-    if (steady && P.var_deg == 4) { run_var_fast<T, VEC, 4, U>(P, L, first, stride, n_end); return; }
-    if (steady && P.var_deg == 2) { run_var_fast<T, VEC, 2, U>(P, L, first, stride, n_end); return; }
-    for (int32_t n = first; n < n_end; n += stride) var_item<T, VEC>(P, L, n);
+    if (s.frame >= 0 && s.fresh)
+        P.synd[(int64_t)ci * P.lanes + lane] = P.synd_in[(int64_t)s.frame * P.C + P.chk_order[ci]];
 }
+
+QR_HD bool lane_needs_refill(const LaneState &s) { return s.retire >= 0 || (s.frame >= 0 && s.fresh); }
 
 }  // namespace qr

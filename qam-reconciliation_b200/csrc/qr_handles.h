@@ -38,6 +38,7 @@ struct qr_decoder {
     int32_t *ctrl = nullptr;              // [CTRL_WORDS]
     unsigned long long *stats = nullptr;  // [2]
     int32_t *work = nullptr;              // [2][kMaxLaneTiles]
+    int32_t *refill_list = nullptr;       // [2][lanes]
     int32_t *h_ctrl = nullptr;            // pinned mirrors
     unsigned long long *h_stats = nullptr;
     cudaStream_t last_stream = nullptr;
@@ -64,6 +65,7 @@ struct qr_mapper {
            *inf_erf = nullptr;
     size_t n_table_doubles = 0;
     double *inv_tab = nullptr;   // F_Y on a uniform grid, see MapperView
+    double *inv_pdf = nullptr;   // its density on the same grid (second half of the same allocation)
     int32_t inv_n = 0;
     double inv_y0 = 0, inv_h = 0;
 };

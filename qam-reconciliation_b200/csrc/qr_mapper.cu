@@ -18,7 +18,7 @@ static MapperView view_of(const qr_mapper *m)
     v.noise_var = m->noise_var; v.sigma = m->sigma; v.s2 = m->s2;
     v.constellation = m->constellation; v.thresholds = m->thresholds; v.probabilities = m->probabilities;
     v.sign_config = m->d_sign; v.FY_thr = m->FY_thr; v.delta = m->delta; v.bare = m->bare;
-    v.inv_tab = m->inv_tab; v.inv_n = m->inv_n; v.inv_y0 = m->inv_y0; v.inv_h = m->inv_h;
+    v.inv_tab = m->inv_tab; v.inv_pdf = m->inv_pdf; v.inv_n = m->inv_n; v.inv_y0 = m->inv_y0; v.inv_h = m->inv_h;
     return v;
 }
 
@@ -63,10 +63,13 @@ __global__ void k_mapper_tables(MapperView m, double *FY_thr, double *delta, dou
 }
 
 // F_Y on a uniform grid (starting points of the fast inverse); one thread per grid point
-__global__ void k_fill_inv_table(MapperView m, double *tab, int32_t n, double y0, double h)
+__global__ void k_fill_inv_table(MapperView m, double *tab, double *pdf, int32_t n, double y0, double h)
 {
     const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) tab[j] = mixture_cdf(m.constellation, m.probabilities, m.order, m.s2, y0 + j * h);
+    if (j < n) {
+        tab[j] = mixture_cdf(m.constellation, m.probabilities, m.order, m.s2, y0 + j * h);
+        pdf[j] = mixture_pdf(m.constellation, m.probabilities, m.order, m.sigma, y0 + j * h);
+    }
 }
 
 // hard decision (+ softening metric) (+ Gray bits) in one pass over y
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(128) k_g_inv(MapperView m, const double *__res
          j += (int64_t)gridDim.x * blockDim.x) {
         const int32_t i = (int32_t)region[j];
         const double target = inv_target(s.sign, s.FYt, s.delta, n_hat[j], i);
-        y_hat[j] = (mode & 1) ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i, InvTable{m.inv_tab, m.inv_n, m.inv_y0, m.inv_h})
+        y_hat[j] = (mode & 1) ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i, InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h})
                               : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
     }
 }
@@ -210,11 +213,12 @@ int qr_mapper_create(int bits_per_symbol, const double *h_constellation, const d
         m->inv_n = 16385;
         m->inv_y0 = h_constellation[0] - 9.0 * m->sigma;
         m->inv_h = (h_constellation[M - 1] + 9.0 * m->sigma - m->inv_y0) / (m->inv_n - 1);
-        QR_CUDA_CHECK(cudaMalloc((void **)&m->inv_tab, m->inv_n * sizeof(double)));
+        QR_CUDA_CHECK(cudaMalloc((void **)&m->inv_tab, 2 * (size_t)m->inv_n * sizeof(double)));
+        m->inv_pdf = m->inv_tab + m->inv_n;
         {
             qr::MapperView v = qr::view_of(m);
             v.inv_tab = nullptr;
-            qr::k_fill_inv_table<<<(m->inv_n + 255) / 256, 256>>>(v, m->inv_tab, m->inv_n, m->inv_y0, m->inv_h);
+            qr::k_fill_inv_table<<<(m->inv_n + 255) / 256, 256>>>(v, m->inv_tab, m->inv_pdf, m->inv_n, m->inv_y0, m->inv_h);
         }
         QR_CUDA_CHECK(cudaGetLastError());
         QR_CUDA_CHECK(cudaDeviceSynchronize());

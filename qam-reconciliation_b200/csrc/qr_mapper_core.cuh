@@ -26,12 +26,14 @@ struct MapperView {
     const double *bare;           // [order*bps]
     // F_Y sampled on a uniform grid y = inv_y0 + j * inv_h, j < inv_n: starting points of the fast inverse
     const double *inv_tab;
+    const double *inv_pdf;
     int32_t inv_n;
     double inv_y0, inv_h;
 };
 
 struct InvTable {
-    const double *F;
+    const double *F;   // F_Y at y0 + j*h
+    const double *f;   // its density at the same points (may be NULL: no Hermite solve)
     int32_t n;
     double y0, h;
 };
@@ -210,11 +212,52 @@ QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, con
                         const InvTable tab)
 {
     if (!(target > 0.0 && target < 1.0)) return g_inv_exact(a, p, order, s2, target, accuracy);
+    double root = 0, f = 1;
+    bool solved = false;
+    // n_hat exactly 0 or 1 puts the target exactly on a stored threshold value: the root is the
+    // decision threshold itself (a dyadic point for the usual constellations, where "mid > root"
+    // must be decided exactly as the reference's "F(mid) > target" is)
+    if (region > 0 && target == FYt[region]) { root = thr[region]; solved = true; }
+    else if (region < order - 1 && target == FYt[region + 1]) { root = thr[region + 1]; solved = true; }
+    if (!solved && tab.n > 1 && tab.f && target >= tab.F[0] && target < tab.F[tab.n - 1]) {
+        // Table solve, no erf/exp at all: F_Y and its density are tabulated on a uniform grid of step
+        // h ~ 2e-3; the cubic Hermite interpolant through (F, f) at the two grid points around the root
+        // reproduces F_Y to h^4 |F^(4)| / 384 ~ 1e-14, so solving the cubic for the target gives the
+        // root to ~1e-14 / f -- far inside the 1e-9 cell the result is snapped to.
+        int32_t lo = 0, hi = tab.n - 1;
+        if (region > 0) {            // the root lies in the decision region: start from its grid bracket
+            const int32_t g = (int32_t)((thr[region] - tab.y0) / tab.h) - 1;
+            if (g > lo && g < hi && tab.F[g] <= target) lo = g;
+        }
+        if (region < order - 1) {
+            const int32_t g = (int32_t)((thr[region + 1] - tab.y0) / tab.h) + 2;
+            if (g > lo && g < hi && tab.F[g] > target) hi = g;
+        }
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (tab.F[mid] <= target) lo = mid; else hi = mid;
+        }
+        const double F0 = tab.F[lo], F1 = tab.F[hi], d0 = tab.f[lo], d1 = tab.f[hi];
+        const double dF = F1 - F0, d = target - F0, A = tab.h * d0, B = tab.h * d1;
+        if (dF > 0 && (d0 < d1 ? d0 : d1) * accuracy > 1e-13) {
+            // G(s) = F_hermite(y_lo + s h) - F0 on s in [0, 1]
+            const double c2 = 3 * dF - 2 * A - B, c3 = A + B - 2 * dF;
+            double sx = d / dF;
+            for (int it = 0; it < 3; ++it) {
+                const double G = sx * (A + sx * (c2 + sx * c3));
+                const double Gp = A + sx * (2 * c2 + 3 * sx * c3);
+                sx -= (G - d) / Gp;
+                sx = sx < 0 ? 0 : (sx > 1 ? 1 : sx);
+            }
+            root = tab.y0 + lo * tab.h + sx * tab.h;
+            f = d0 + sx * (d1 - d0);
+            solved = true;
+        }
+    }
+    if (!solved) {
     double rlo, rhi, y;
     bool presolved = false;
     if (tab.n > 1 && target >= tab.F[0] && target < tab.F[tab.n - 1]) {
-        // table lookup: F[lo] <= target < F[hi] brackets the root within one grid step, linear
-        // interpolation lands within ~1e-5 of it -- close enough for one cubic (Halley) step
         int32_t lo = 0, hi = tab.n - 1;
         while (hi - lo > 1) {
             const int32_t mid = (lo + hi) >> 1;
@@ -274,16 +317,8 @@ QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, con
         if ((double)yf > rlo && (double)yf < rhi) y = (double)yf;
     }
     const double c0 = 0.3989422804014327 / sigma, c1 = c0 / (sigma * sigma);
-    double root = y;
-    double f = 1;
-    // n_hat exactly 0 or 1 puts the target exactly on a stored threshold value: the root is the
-    // decision threshold itself (a dyadic point for the usual constellations, where "mid > root"
-    // must be decided exactly as the reference's "F(mid) > target" is)
-    const bool at_lo = region > 0 && target == FYt[region];
-    const bool at_hi = region < order - 1 && target == FYt[region + 1];
-    if (at_lo) root = thr[region];
-    if (at_hi) root = thr[region + 1];
-    for (int it = 0; it < 100 && !(at_lo || at_hi); ++it) {
+    root = y;
+    for (int it = 0; it < 100; ++it) {
         double F = 0, fp = 0;
         f = 0;
         for (int k = 0; k < order; ++k) {
@@ -310,6 +345,7 @@ QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, con
         if (safe && fabs(step) <= (cubic ? 1e-5 : 3e-8) * sigma) break;
         if ((rhi - rlo) <= 4e-16 * fmax(1.0, fabs(y))) break;
     }
+    }   // !solved
     // Deep in the tails F is flat at the resolution of a double (one ulp of F spans f^-1 * 1e-16 in y):
     // there the reference's answer is set by the rounding of F, not by the root.  Replay it exactly.
     if (!(f * accuracy > 1e-14)) return g_inv_exact(a, p, order, s2, target, accuracy);
@@ -328,7 +364,17 @@ QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, con
     // cell can be computed directly and the result is bit-identical to running the loop.
     const double W = hi - lo;
     int k = 0;
-    for (double wd = W; wd > accuracy && k < kMaxHalvings; wd *= 0.5) ++k;
+    {
+        // halvings until W / 2^k <= accuracy.  W is a power of two here (0/1 or doubled bounds), so k
+        // follows from the exponents; the two probes settle the rounding of the estimate exactly.
+        int ew = 0, ea = 0;
+        (void)frexp(W, &ew);
+        (void)frexp(accuracy, &ea);
+        k = ew - ea + 1;
+        if (k < 0) k = 0;
+        while (k > 0 && ldexp(W, -(k - 1)) <= accuracy) --k;
+        while (k < kMaxHalvings && ldexp(W, -k) > accuracy) ++k;
+    }
     if (k > 52) {   // not reachable for accuracy = 1e-9 and finite brackets; keep the loop for safety
         for (int it = 0; (hi - lo) > accuracy && it < kMaxHalvings; ++it) {
             const double mid = (hi + lo) / 2;
@@ -397,7 +443,7 @@ QR_HD void demap_symbol(const MapperView &m, const TablesRef &s, double nv, int3
     for (int i = 0; i < m.order; ++i) {
         const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
         const double yh = fast ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i,
-                                            InvTable{m.inv_tab, m.inv_n, m.inv_y0, m.inv_h})
+                                            InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h})
                                : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
         double sum = 0;
         for (int k = 0; k < j; ++k) {

@@ -57,14 +57,24 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
     P.llr_in = llr; P.llr_in_f64 = llr_dtype == QR_F64; P.synd_in = synd;
     P.frames = frames; P.maxiter = maxiter; P.success = success; P.iters = iters;
     P.post_out = post; P.post_out_f64 = post_dtype == QR_F64;
-    P.ctrl = ctrl.data(); P.stats = stats; P.work = nullptr;
+    P.ctrl = ctrl.data(); P.stats = stats; P.work = nullptr; P.refill_list = nullptr;
     for (int l = 0; l < lanes; ++l) {
         LaneState s;
-        s.frame = l < frames ? l : -1; s.iter = 0; s.fresh = s.frame >= 0; s.pad = 0;
+        s.frame = l < frames ? l : -1; s.iter = 0; s.fresh = s.frame >= 0; s.retire = -1;
         st[l] = s; st[lanes + l] = s;
     }
     ctrl[CTRL_NEXT_FRAME] = (int32_t)std::min<int64_t>(lanes, frames);
     ctrl[CTRL_REMAINING] = (int32_t)frames;
+    ctrl[CTRL_FIN_STEP] = -1;
+    auto refill = [&](int buf) {
+        for (int lane = 0; lane < lanes; ++lane) {
+            const LaneState s = P.st[buf][lane];
+            if (!lane_needs_refill(s)) continue;
+            for (int32_t n = 0; n < g.N; ++n) refill_var_elem<T>(P, s, lane, n);
+            for (int32_t ci = 0; ci < g.C; ++ci) refill_chk_elem<T>(P, s, lane, ci);
+        }
+    };
+    refill(0);
     const int LV = lanes / VEC;
     int64_t step = 0;
     for (; ctrl[CTRL_REMAINING] > 0; ++step) {
@@ -94,8 +104,9 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
             LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
             decide_lanes<T, VEC>(P, cur, L);
             for (int32_t t = 0; t < 5; ++t) run_var_range<T, VEC>(P, L, t, 5, (int32_t)g.N);
-            bookkeep_lanes<T, VEC>(P, cur, L);
+            bookkeep_lanes<T, VEC>(P, cur, (int32_t)step, L);
         }
+        if (ctrl[CTRL_FIN_STEP] == step) refill(cur ^ 1);
     }
     if (steps_out) *steps_out = step;
     return 0;
@@ -150,9 +161,13 @@ void emu_demap(int bps, const double *a, const double *thr, const double *p, dou
     // the same starting table libqamrecon builds on the device (qr_mapper_create)
     const int32_t tn = 16385;
     const double ty0 = a[0] - 9.0 * sigma, th = (a[M - 1] + 9.0 * sigma - ty0) / (tn - 1);
-    std::vector<double> tabF(tn);
-    for (int32_t j = 0; j < tn; ++j) tabF[j] = mixture_cdf(a, p, M, s2, ty0 + j * th);
-    const InvTable tab{(mode & 4) ? nullptr : tabF.data(), (mode & 4) ? 0 : tn, ty0, th};
+    std::vector<double> tabF(tn), tabf(tn);
+    for (int32_t j = 0; j < tn; ++j) {
+        tabF[j] = mixture_cdf(a, p, M, s2, ty0 + j * th);
+        tabf[j] = mixture_pdf(a, p, M, sigma, ty0 + j * th);
+    }
+    // mode bit 2: no table at all; bit 3: table of F only (no Hermite solve)
+    const InvTable tab{(mode & 4) ? nullptr : tabF.data(), (mode & 12) ? nullptr : tabf.data(), (mode & 4) ? 0 : tn, ty0, th};
     for (int64_t s = 0; s < n; ++s) {
         for (int i = 0; i < M; ++i) {
             const double target = inv_target(sign, FYt.data(), delta.data(), n_hat[s], i);
