@@ -48,13 +48,21 @@ def parse():
     ap.add_argument("--snr", type=float, default=3.0, help="Es/N0 [dB]; 3.0 is below the waterfall")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--demap", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--lanes", type=int, default=0, help="frames resident in the decoder (0 = library default)")
-    ap.add_argument("--schedule", type=int, default=0, help="0 persistent kernel, 1 launch per phase")
+    ap.add_argument("--lanes", type=int, default=-1,
+                    help="frames resident in the decoder (0 = library default; -1 = 1024 for the fused schedule, else 0)")
+    ap.add_argument("--schedule", type=int, default=-1,
+                    help="0 persistent two-phase kernel, 1 launch per phase, 2 fused flooding iteration (persistent); "
+                         "-1 = 2 in fp32, 0 in fp64")
     ap.add_argument("--n", type=int, default=N_CODE, help="code length (default: the metric's 64800)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames per CPU worker (0 = auto)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.schedule < 0:
+        a.schedule = 2 if a.precision == "fp32" else 0
+    if a.lanes < 0:
+        a.lanes = 1024 if a.schedule == 2 else 0
+    return a
 
 
 def peaks():
@@ -367,8 +375,9 @@ def ours(a):
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_persistent (decoder, one launch per batch)" if a.schedule == 0
-                else "k_check+k_var", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kname = {0: "k_persistent (decoder, one launch per batch)", 1: "k_check+k_var",
+             2: "k_fused (decoder, fused flooding iteration, one launch per batch)"}[a.schedule]
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fi * bytes_per_frame_iter, "launch_ms": k_ms,
                 "edge_updates_per_s": fi * E / (k_ms / 1e3), "frame_iterations_per_launch": fi,
@@ -417,7 +426,7 @@ def ours(a):
             "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f64", "data": "synthetic",
             "config": {"workload": workload_name(n, a.snr),
                        "frames_per_gpu_per_step": B, "demap": a.demap, "decoder_lanes": a.lanes or 512,
-                       "schedule": "persistent" if a.schedule == 0 else "launch",
+                       "schedule": {0: "persistent", 1: "launch", 2: "fused"}[a.schedule],
                        "l2_policy": f"{n_sets} alternating input sets of {B * S * 16 / 1e9:.1f} GB each (>> 126 MB L2)"},
             "info_gbit_per_s": value * K / 1e9,
             "avg_iterations": fi / B, "ber": cnt[0] / max(1, cnt[4] * K), "fer": cnt[1] / max(1, cnt[4]),

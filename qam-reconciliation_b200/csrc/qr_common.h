@@ -56,6 +56,10 @@ struct qr_graph {
     std::vector<int32_t> var_ptr;    // [N+1]
     std::vector<int32_t> var_slot;   // [E]   per variable, CSR slots in ascending edge id
     std::vector<qr::CheckBin> bins;
+    // fused schedule (var_deg == 3 only): per CSR slot {variable | own position << 28, the variable's three
+    // CSR slots in ascending edge id}; empty otherwise
+    std::vector<int32_t> slot_nbr;   // [4 * E]
+    int32_t *d_slot_nbr = nullptr;
     // device copies
     int32_t *d_chk_order = nullptr, *d_chk_ptr = nullptr, *d_slot_var = nullptr;
     int32_t *d_var_ptr = nullptr, *d_var_slot = nullptr;

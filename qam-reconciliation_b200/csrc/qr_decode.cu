@@ -354,6 +354,7 @@ __global__ void k_init_batch(LaneState *st0, LaneState *st1, int32_t *unsat0, in
         ctrl[CTRL_FIN_STEP] = -1;
         ctrl[CTRL_REFILL_CNT + 0] = (int32_t)min((int64_t)lanes, frames);
         ctrl[CTRL_REFILL_CNT + 1] = 0;
+        ctrl[6] = 0;   // CTRL_ARRIVE of the fused schedule
         stats[0] = 0;
         stats[1] = 0;
     }
@@ -425,7 +426,7 @@ template <typename T, int DSEL, int VEC = Prec<T>::VEC>
 static int run_batch_t(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream)
 {
     const Tiling tl = make_tiling<VEC>(P.lanes);
-    if (d->schedule == QR_SCHED_PERSISTENT) {
+    if (d->schedule != QR_SCHED_LAUNCH) {
         int per_sm = 0;
         QR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<T, VEC, DSEL>,
                                                                     kBlock, 0));
@@ -462,8 +463,14 @@ static int run_batch_t(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t str
 }
 
 template <typename T>
+int run_batch_fused(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream);   // qr_decode_fused.cu
+bool fused_eligible(const qr_graph *g);
+
+template <typename T>
 static int run_batch(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream)
 {
+    if (d->schedule == QR_SCHED_FUSED || (d->schedule == QR_SCHED_AUTO && fused_eligible(d->g)))
+        return run_batch_fused<T>(d, P, stream);
     if constexpr (sizeof(T) == 4) {
         // narrower lane vectors (more, lighter threads) -- experimental, QAMRECON_VEC=1|2
         if (d->regular_degree == 6 && d->vec == 1) return run_batch_t<T, 6, 1>(d, P, stream);
@@ -514,6 +521,11 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
         d->lanes = (int32_t)lanes;
         d->regular_degree = (g->bins.size() == 1 && g->bins[0].degree == 6) ? 6 : 0;
         if (const char *v = getenv("QAMRECON_VEC")) d->vec = atoi(v);
+        if (const char *v = getenv("QAMRECON_FUSED_TILE")) d->fused_tile = atoi(v);
+        if (const char *v = getenv("QAMRECON_FUSED_HINTS")) d->fused_hints = atoi(v);
+        if (const char *v = getenv("QAMRECON_FUSED_PIPE")) d->fused_pipe = atoi(v);
+        if (const char *v = getenv("QAMRECON_FUSED_PREFETCH")) d->fused_prefetch = atoi(v);
+        if (const char *v = getenv("QAMRECON_FUSED_RPC")) d->fused_rpc = atoi(v);
         const size_t L = (size_t)lanes;
         QR_CUDA_CHECK(cudaMalloc(&d->c2v, (size_t)g->E * L * w));
         QR_CUDA_CHECK(cudaMalloc(&d->post, (size_t)g->N * L * w));
@@ -548,7 +560,7 @@ void qr_decoder_destroy(qr_decoder *d)
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(d->device);
-    cudaFree(d->c2v); cudaFree(d->post); cudaFree(d->llr); cudaFree(d->synd);
+    cudaFree(d->c2v); cudaFree(d->c2v2); cudaFree(d->post); cudaFree(d->llr); cudaFree(d->synd);
     cudaFree(d->st); cudaFree(d->unsat); cudaFree(d->ctrl); cudaFree(d->stats); cudaFree(d->work); cudaFree(d->refill_list);
     cudaFree(d->pipe_buf);
     cudaFree(d->dev_buf);
@@ -566,8 +578,11 @@ void qr_decoder_destroy(qr_decoder *d)
 int qr_decoder_set_schedule(qr_decoder *d, int schedule)
 {
     if (!d) return qr::fail(QR_ERR_INVALID, "null decoder");
-    if (schedule != QR_SCHED_PERSISTENT && schedule != QR_SCHED_LAUNCH)
+    if (schedule != QR_SCHED_PERSISTENT && schedule != QR_SCHED_LAUNCH && schedule != QR_SCHED_FUSED &&
+        schedule != QR_SCHED_AUTO)
         return qr::fail(QR_ERR_INVALID, "unknown schedule");
+    if (schedule == QR_SCHED_FUSED && !qr::fused_eligible(d->g))
+        return qr::fail(QR_ERR_INVALID, "fused schedule needs every variable of degree 3 and check degrees <= 8");
     d->schedule = schedule;
     return QR_OK;
 }

@@ -90,6 +90,22 @@ inline int build_host_tables(qr_graph &g, const int64_t *vid, const int64_t *cid
             g.var_slot[g.var_ptr[v] + fill[v]++] = edge_slot[e];
         }
     }
+    // neighbour table of the fused schedule: what a check needs to rebuild post[v] = llr[v] + sum c2v
+    // (decoder.pyx:291-293) of each of its variables without a stored posterior
+    g.slot_nbr.clear();
+    if (g.var_deg == 3 && N < (int64_t(1) << 28)) {
+        g.slot_nbr.assign(4 * (size_t)E, 0);
+        for (int64_t s = 0; s < E; ++s) {
+            const int32_t v = g.slot_var[s];
+            int32_t own = -1;
+            for (int j = 0; j < 3; ++j) {
+                const int32_t t = g.var_slot[g.var_ptr[v] + j];
+                g.slot_nbr[4 * s + 1 + j] = t;
+                if (t == s) own = j;
+            }
+            g.slot_nbr[4 * s] = v | (own << 28);
+        }
+    }
     return QR_OK;
 }
 

@@ -32,6 +32,12 @@ struct qr_decoder {
     int regular_degree = 0;  // > 0: check-regular graph with a specialised kernel
     int vec = 0;             // 0: default lanes per thread; 1 or 2: narrower (fp32 only, experimental)
     void *c2v = nullptr, *post = nullptr, *llr = nullptr;
+    void *c2v2 = nullptr;    // second message buffer of QR_SCHED_FUSED (allocated on first use)
+    int fused_tile = 32;     // lanes per L2 tile of the fused schedule (32, 64 or 128)
+    int fused_pipe = 0;      // staging experiments (only with -DQR_FUSED_EXPERIMENTS): 1/2 cp.async stages, 3 TMA bulk rows
+    int fused_prefetch = 0;  // 1: sequential L2 prefetch of the next tile (measured slower on B200)
+    int fused_rpc = 4;       // checks per thread and claim of the register-staged fused phase
+    int fused_hints = 1;     // L2 policy of the fused schedule: 0 none, 1 stores evict-first, 2 + loads evict-last
     uint8_t *synd = nullptr;
     qr::LaneState *st = nullptr;          // [2][lanes]
     int32_t *unsat = nullptr;             // [2][lanes]

@@ -158,8 +158,11 @@ extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, in
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     qr::DeviceGuard guard(d->device);
 
-    // chunking: at least two decoder fills per chunk, about eight chunks per batch
+    // chunking: about eight chunks per batch and two decoder fills per chunk (continuous batching needs more
+    // frames than lanes to keep the lanes busy), but never fewer than four chunks when the batch allows it --
+    // with fewer, the first chunk's upload and the last chunk's download are no longer hidden
     int64_t chunk = std::max<int64_t>(2 * (int64_t)d->lanes, (frames + 7) / 8);
+    chunk = std::min<int64_t>(chunk, std::max<int64_t>((int64_t)d->lanes, (frames + 3) / 4));
     chunk = std::min(chunk, frames);
     const int64_t n_chunks = (frames + chunk - 1) / chunk;
     const int n_sets = n_chunks > 1 ? 2 : 1;

@@ -13,6 +13,7 @@
 #include "../../qam-reconciliation_b200/csrc/qr_common.h"
 #include "../../qam-reconciliation_b200/csrc/qr_graph_build.h"
 #include "../../qam-reconciliation_b200/csrc/qr_decode_core.cuh"
+#include "../../qam-reconciliation_b200/csrc/qr_decode_fused.cuh"
 #include "../../qam-reconciliation_b200/csrc/qr_mapper_core.cuh"
 
 namespace qr {
@@ -112,6 +113,79 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
     return 0;
 }
 
+// QR_SCHED_FUSED: one fused phase per step over tile-major arrays, bookkeeping, refill
+template <typename T, int VEC>
+static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *llr, int llr_dtype,
+                              const uint8_t *synd, int64_t frames, int maxiter, uint8_t *success, int32_t *iters,
+                              void *post, int post_dtype, int64_t *steps_out)
+{
+    if (g.slot_nbr.empty() || g.max_cdeg > kFusedMaxCheckDegree || lanes % tl) return -2;
+    std::vector<T> c2v0((size_t)g.E * lanes, (T)1e30), c2v1((size_t)g.E * lanes, (T)-3e30), llrw((size_t)g.N * lanes, (T)3e29);
+    std::vector<uint8_t> syndw((size_t)g.C * lanes, 0xff);
+    std::vector<LaneState> st(2 * lanes);
+    std::vector<int32_t> unsat(2 * lanes, 0), ctrl(CTRL_WORDS, 0);
+    unsigned long long stats[2] = {0, 0};
+    FusedParams<T> F;
+    DecodeParams<T> &P = F.P;
+    P.bins = g.bins.data(); P.n_bins = (int32_t)g.bins.size();
+    P.chk_order = g.chk_order.data(); P.slot_var = g.slot_var.data();
+    P.var_ptr = g.var_ptr.data(); P.var_slot = g.var_slot.data();
+    P.N = g.N; P.C = g.C; P.E = g.E; P.lanes = lanes; P.var_deg = g.var_deg;
+    P.c2v = nullptr; P.post = nullptr; P.llr = llrw.data(); P.synd = syndw.data();
+    P.st[0] = st.data(); P.st[1] = st.data() + lanes;
+    P.unsat[0] = unsat.data(); P.unsat[1] = unsat.data() + lanes;
+    P.llr_in = llr; P.llr_in_f64 = llr_dtype == QR_F64; P.synd_in = synd;
+    P.frames = frames; P.maxiter = maxiter; P.success = success; P.iters = iters;
+    P.post_out = post; P.post_out_f64 = post_dtype == QR_F64;
+    P.ctrl = ctrl.data(); P.stats = stats; P.work = nullptr; P.refill_list = nullptr;
+    F.nbr = reinterpret_cast<const Nbr4 *>(g.slot_nbr.data());
+    F.c2v[0] = c2v0.data(); F.c2v[1] = c2v1.data();
+    F.tl = tl; F.tiles = lanes / tl; F.hints = 0; F.prefetch = 0; F.rows_per_claim = 2;
+    for (int l = 0; l < lanes; ++l) {
+        LaneState s;
+        s.frame = l < frames ? l : -1; s.iter = 0; s.fresh = s.frame >= 0; s.retire = -1;
+        st[l] = s; st[lanes + l] = s;
+    }
+    ctrl[CTRL_NEXT_FRAME] = (int32_t)std::min<int64_t>(lanes, frames);
+    ctrl[CTRL_REMAINING] = (int32_t)frames;
+    ctrl[CTRL_FIN_STEP] = -1;
+    auto refill = [&](int buf, int cur) {
+        for (int lane = 0; lane < lanes; ++lane) {
+            const LaneState s = P.st[buf][lane];
+            if (!lane_needs_refill(s)) continue;
+            for (int32_t n = 0; n < g.N; ++n) fused_refill_var_elem<T>(F, cur, s, lane, n);
+            for (int32_t ci = 0; ci < g.C; ++ci) fused_refill_chk_elem<T>(F, s, lane, ci);
+        }
+    };
+    refill(0, 0);
+    int64_t step = 0;
+    for (; ctrl[CTRL_REMAINING] > 0; ++step) {
+        if (step > (frames + lanes) * (int64_t)(maxiter + 3)) return -1;
+        const int cur = step & 1;
+        for (int tile = 0; tile < F.tiles; ++tile) {
+            const TileView<T> V = tile_view(F, cur, tile);
+            for (int tx = 0; tx < tl / VEC; ++tx) {
+                const LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, (tile * tl) / VEC + tx);
+                if (!L.active) continue;
+                uint32_t bad = 0;
+                for (const CheckBin &bin : g.bins)
+                    for (int32_t t = 0; t < 3; ++t)
+                        bad |= run_fused_bin_any<T, VEC>(V, F.nbr, L, tx * VEC, bin, t, 3, 0, 0);
+                for (int k = 0; k < VEC; ++k)
+                    if (bad >> k & 1) P.unsat[cur][L.l0 + k] = 1;
+            }
+        }
+        for (int jv = 0; jv < lanes / VEC; ++jv) {
+            LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
+            decide_lanes<T, VEC>(P, cur, L);
+            bookkeep_lanes<T, VEC>(P, cur, (int32_t)step, L);
+        }
+        if (ctrl[CTRL_FIN_STEP] == step) refill(cur ^ 1, cur);
+    }
+    if (steps_out) *steps_out = step;
+    return 0;
+}
+
 extern "C" {
 
 const char *emu_last_error() { return qr::g_err.c_str(); }
@@ -144,6 +218,20 @@ int emu_decode(const int64_t *vid, const int64_t *cid, int64_t E, int precision,
                                        iters, post, post_dtype, steps);
     return emu_decode_t<float, 4>(g, lanes, generic != 0, llr, llr_dtype, synd, frames, maxiter, success, iters,
                                   post, post_dtype, steps);
+}
+
+int emu_decode_fused(const int64_t *vid, const int64_t *cid, int64_t E, int precision, int lanes, int tile_lanes,
+                     const void *llr, int llr_dtype, const uint8_t *synd, int64_t frames, int maxiter,
+                     uint8_t *success, int32_t *iters, void *post, int post_dtype, int64_t *steps)
+{
+    qr_graph g;
+    int rc = build_host_tables(g, vid, cid, E);
+    if (rc) return rc;
+    if (precision == QR_F64)
+        return emu_decode_fused_t<double, 2>(g, lanes, tile_lanes, llr, llr_dtype, synd, frames, maxiter, success,
+                                             iters, post, post_dtype, steps);
+    return emu_decode_fused_t<float, 4>(g, lanes, tile_lanes, llr, llr_dtype, synd, frames, maxiter, success, iters,
+                                        post, post_dtype, steps);
 }
 
 // mapper arithmetic: mode bit 0 = fast inverse, bit 1 = corrected exponent

@@ -44,6 +44,23 @@ def emu_decode(vid, cid, llr, synd, maxiter, precision=F64, lanes=32, generic=0,
     return ok, it, post, steps.value
 
 
+def emu_decode_fused(vid, cid, llr, synd, maxiter, precision=F64, lanes=32, tile_lanes=32, post_dtype=F64):
+    L = load()
+    vid = np.ascontiguousarray(vid, dtype=np.int64); cid = np.ascontiguousarray(cid, dtype=np.int64)
+    llr = np.ascontiguousarray(llr); synd = np.ascontiguousarray(synd, dtype=np.uint8)
+    frames, N = llr.shape
+    ok = np.full(frames, 255, dtype=np.uint8); it = np.full(frames, -1, dtype=np.int32)
+    post = np.zeros((frames, N), dtype=np.float64 if post_dtype == F64 else np.float32)
+    steps = C.c_int64(0)
+    rc = L.emu_decode_fused(ptr(vid), ptr(cid), C.c_int64(vid.size), precision, lanes, tile_lanes, ptr(llr),
+                            F64 if llr.dtype == np.float64 else F32, ptr(synd), C.c_int64(frames), maxiter, ptr(ok),
+                            ptr(it), ptr(post), post_dtype, C.byref(steps))
+    if rc == -2:
+        return None   # graph not eligible for the fused schedule (variable degree != 3 or a check degree > 8)
+    assert rc == 0, L.emu_last_error()
+    return ok, it, post, steps.value
+
+
 def test_graph_tables_invariants():
     L = load()
     rng = np.random.default_rng(0)
@@ -111,6 +128,58 @@ def test_emulated_fp64_decoder_chain_bit_exact(path, generic):
             ok, it, post, _ = emu_decode(g["vid"], g["cid"], llr, synd, int(g["maxiter"]), generic=generic)
             assert np.array_equal(ok, g[f"s{si}_{mode}ok"]) and np.array_equal(it, g[f"s{si}_{mode}it"])
             assert same_bits(post, g[f"s{si}_{mode}post"])
+
+
+def test_emulated_fused_schedule_chain_bit_exact():
+    """QR_SCHED_FUSED (no stored posteriors, two message buffers, tile-major lanes) restates the same
+    arithmetic: fp64 results bit-identical to the compiled reference on every eligible fixture."""
+    seen = 0
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "chain_*.npz"))):
+        g = np.load(path)
+        for si in range(len(g["snrs"])):
+            for mode, lk, sk in (("", "lappr", "synd"), ("hard_", "hard_lappr", "synd"), ("dir_", "dir_lappr", "dir_synd")):
+                llr = g[f"s{si}_{lk}"]; synd = g[f"s{si}_{sk}"]
+                if not np.all(np.isfinite(llr)):
+                    continue
+                for lanes, tl in ((32, 32), (64, 32), (64, 64)):
+                    r = emu_decode_fused(g["vid"], g["cid"], llr, synd, int(g["maxiter"]), lanes=lanes, tile_lanes=tl)
+                    if r is None:
+                        continue
+                    ok, it, post, _ = r
+                    assert np.array_equal(ok, g[f"s{si}_{mode}ok"]) and np.array_equal(it, g[f"s{si}_{mode}it"])
+                    assert same_bits(post, g[f"s{si}_{mode}post"])
+                    seen += 1
+    assert seen >= 9
+
+
+def test_emulated_fused_schedule_edge_cases_match_two_phase():
+    """max_iterations 0/1, already-consistent input, -0.0, more frames than lanes: fused == two-phase == oracle."""
+    from qamreconciliation import codes
+    rng = np.random.default_rng(11)
+    vid, cid = codes.regular_ldpc(96, 3, 6, seed=5)
+    dec = orc.Decoder(vid, cid); mat = orc.Matrix(vid, cid)
+    frames = 75
+    word = rng.integers(0, 2, size=(frames, 96)).astype(np.uint8)
+    sigma = rng.choice([0.5, 0.8, 1.1], size=(frames, 1))
+    llr = 2 * ((1 - 2.0 * word) + sigma * rng.normal(size=word.shape)) / sigma ** 2
+    synd = np.array([mat.eval_syndrome(w) for w in word])
+    synd[::3] ^= rng.integers(0, 2, size=synd[::3].shape).astype(np.uint8)
+    llr[5] = np.where(word[5] == 1, -3.0, 3.0); synd[5] = mat.eval_syndrome(word[5])
+    llr[7, :4] = -0.0
+    for maxiter in (0, 1, 12):
+        want = [dec.decode(llr[f], synd[f], maxiter) for f in range(frames)]
+        for lanes, tl in ((32, 32), (64, 32), (128, 64)):
+            ok, it, post, _ = emu_decode_fused(vid, cid, llr, synd, maxiter, lanes=lanes, tile_lanes=tl)
+            assert [int(o) for o in ok] == [w[0] for w in want]
+            assert [int(i) for i in it] == [w[1] for w in want]
+            for f in range(frames):
+                assert same_bits(post[f], want[f][2]), (maxiter, lanes, f)
+    # fp32: same decisions as the two-phase fp32 schedule, frame by frame
+    ok2, it2, post2, _ = emu_decode(vid, cid, llr.astype(np.float32), synd, 12, precision=F32, post_dtype=F32)
+    ok3, it3, post3, _ = emu_decode_fused(vid, cid, llr.astype(np.float32), synd, 12, precision=F32, lanes=64,
+                                          tile_lanes=32, post_dtype=F32)
+    assert np.array_equal(ok2, ok3) and np.array_equal(it2, it3)
+    np.testing.assert_allclose(post3, post2, rtol=1e-5, atol=1e-5)
 
 
 def test_emulated_continuous_batching_matches_oracle():

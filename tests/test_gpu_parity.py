@@ -207,7 +207,7 @@ def test_mapper_fixture(qr, path):
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "chain_*.npz"))))
-@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("schedule", [0, 1, 3])   # 3 = fused where the graph allows it, else persistent
 def test_chain_fixture(qr, path, schedule):
     """Whole frames as sims/reconciliation.pyx:127-153 chains them; decoder fed the reference's LLRs."""
     g = np.load(path)
@@ -248,7 +248,7 @@ def bpsk_frames(orc, vid, cid, frames, sigmas, seed, flip_every=0):
     return word, llr, synd
 
 
-@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("schedule", [0, 1, 2])
 @pytest.mark.parametrize("lanes", [32, 64])
 def test_fp64_batch_matches_oracle_with_refill(qr, orc, schedule, lanes):
     """More frames than lanes, widely different convergence times: every frame equals the oracle."""
@@ -295,7 +295,7 @@ def test_fp32_batch_tracks_oracle(qr, orc):
     word, llr, synd = bpsk_frames(orc, vid, cid, frames, [0.80, 0.84], seed=4)
     ook, oit, opost = orc.Decoder(vid, cid).decode_frames(llr, synd, 50)
     dec = qr.Decoder(vid, cid)
-    for schedule in (0, 1):
+    for schedule in (0, 1, 2):
         ok, it, post = dec.decode_batch(torch.tensor(llr, dtype=torch.float32), synd, 50, precision="fp32", schedule=schedule)
         ok, it, post = ok.cpu().numpy(), it.cpu().numpy(), post.cpu().numpy()
         assert post.dtype == np.float32

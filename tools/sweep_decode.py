@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--precisions", default="fp32")
     ap.add_argument("--maxiter", type=int, default=50)
     ap.add_argument("--stages", action="store_true")
+    ap.add_argument("--fused", default="32:1", help="tile:hints[:pipe[:prefetch[:rows_per_claim]]] combinations tried for schedule 2 (fused)")
     a = ap.parse_args()
     n, B = a.n, a.frames
     vid, cid = codes.regular_ldpc(n, 3, 6, seed=1)
@@ -61,11 +62,18 @@ def main():
         bpi = 4 * E * w + 2 * n * w + C
         inp = llr if prec == "fp32" else llr.double()
         for sched in [int(s) for s in a.schedules.split(",")]:
+          for combo in (a.fused.split(",") if sched == 2 else [""]):
+            if combo:
+                parts = (combo.split(":") + ["0", "0", "2"])[:5] if combo.count(":") < 4 else combo.split(":")
+                os.environ["QAMRECON_FUSED_RPC"] = parts[4]
+                os.environ["QAMRECON_FUSED_PREFETCH"] = parts[3]
+                os.environ["QAMRECON_FUSED_TILE"], os.environ["QAMRECON_FUSED_HINTS"] = parts[0], parts[1]
+                os.environ["QAMRECON_FUSED_PIPE"] = parts[2]
             for lanes in [int(s) for s in a.lanes.split(",")]:
                 t, (ok, it, post) = timeit(lambda: dec.decode_batch(inp, synd, a.maxiter, precision=prec, lanes=lanes,
                                                                    schedule=sched))
                 fi, steps = dec.last_stats(prec, lanes)
-                print(f"{prec} sched {sched} lanes {lanes:5d}: {t:9.2f} ms  {B / t * 1e3:9.0f} frames/s  "
+                print(f"{prec} sched {sched}{' ' + combo if combo else ''} lanes {lanes:5d}: {t:9.2f} ms  {B / t * 1e3:9.0f} frames/s  "
                       f"{fi * bpi / t / 1e6:8.0f} GB/s alg  avg it {fi / B:5.1f}  steps {steps}  ok {int(ok.sum())}",
                       flush=True)
                 # free the workspace of this lane count before the next one
