@@ -164,6 +164,27 @@ int qr_bare_llr(const qr_mapper *m, const int64_t *d_tx_index, int64_t n, void *
 int qr_direct_llr(const qr_mapper *m, const double *d_y, int64_t n, double two_variance,
                   void *d_llr, int llr_dtype, void *stream);
 
+/* ---------------------------------------------------------------- rest of the NoiseMapper surface
+ * Sign rule of g / map_noise / g_inv / demap_noise / the two formulations below: NoiseMapper uses its
+ * sign_config (the default after qr_mapper_create); NoiseMapperFlipSign (noisemapper.pyx:775-797) uses 1 on the
+ * lower half of the alphabet, NoiseMapperAntiFlipSign (:798-816) 1 on the upper half.  g_inv_search and
+ * demap_lappr keep the constructor's sign_config, as in the reference (the subclasses do not override them). */
+int qr_mapper_set_g_sign(qr_mapper *m, const uint8_t *h_sign_g);
+/* the dense grid of noisemapper.pyx:135-144: y_range = numpy.linspace(y_low, y_high, n_points), F_Y on it
+ * (NoiseMapper.F_Y, :264-275: uniform weights).  Needed by qr_demap_noise / qr_demap_lappr_variant. */
+int qr_mapper_build_grid(qr_mapper *m, double y_low, double y_high, int64_t n_points);
+/* NoiseMapper.y_range / F_Y_values (noisemapper.pyx:254-261); host arrays of n_points, NULL to skip */
+int qr_mapper_grid(const qr_mapper *m, int64_t *n_points, double *h_y_range, double *h_F_Y);
+/* NoiseMapper.F_Y (noisemapper.pyx:264-275) and the module function F_Z (:70-80) */
+int qr_F_Y(const qr_mapper *m, const double *d_y, int64_t n, double *d_out, void *stream);
+int qr_F_Z(const double *d_z, int64_t n, double mu, double sigma, double *d_out, void *stream);
+/* NoiseMapper.demap_noise = g_inv per element (noisemapper.pyx:391-404, :295-307, __interp :47-63) */
+int qr_demap_noise(const qr_mapper *m, const double *d_n_hat, const int64_t *d_symb, int64_t n, double *d_y_hat,
+                   void *stream);
+/* variant 1: demap_lappr_simplified_array (noisemapper.pyx:563-621); 2: demap_lappr_sofisticated_array (:624-766) */
+int qr_demap_lappr_variant(const qr_mapper *m, int variant, const double *d_n_hat, const int64_t *d_tx_index,
+                           int64_t n, double *d_llr, void *stream);
+
 /* ---------------------------------------------------------------- whole path, device buffers
  * The chain of sims/reconciliation.pyx:129-153 (mode 0 soft reverse, 1 hard reverse :300-308,
  * 2 soft direct :214-227) for `frames` frames whose channel outputs d_y [frames][S] and Alice's

@@ -36,6 +36,13 @@ def lib():
         L.qro_demap_lappr_array.argtypes = [C.c_void_p, _dp, _lp, C.c_long, C.c_int, _dp]
         L.qro_bare_llr.argtypes = [C.c_void_p, _lp, C.c_long, _dp]
         L.qro_direct_llr.argtypes = [_dp, C.c_long, _dp, C.c_int, C.c_double, _dp]
+        L.qro_F_Z.argtypes = [_dp, C.c_long, C.c_double, C.c_double, _dp]
+        L.qro_F_Y.argtypes = [C.c_void_p, _dp, C.c_long, _dp]
+        L.qro_grid.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_long, _dp, _dp]
+        L.qro_g_inv.argtypes = [C.c_void_p, _bp, _dp, _dp, C.c_long, _dp, _lp, C.c_long, _dp]
+        L.qro_map_noise_sign.argtypes = [C.c_void_p, _bp, _dp, _lp, C.c_long, _dp]
+        L.qro_demap_simplified.argtypes = [C.c_void_p, _bp, _dp, _dp, C.c_long, _dp, _lp, C.c_long, _dp]
+        L.qro_demap_sofisticated.argtypes = [C.c_void_p, _bp, _dp, _dp, C.c_long, _dp, _lp, C.c_long, _dp]
         L.qro_gray_table.argtypes = [C.c_int, _bp]
         L.qro_alphabet.argtypes = [C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp]
         L.qro_hard_decide_index.argtypes = [_dp, C.c_int, _dp, C.c_long, _lp]
@@ -110,8 +117,15 @@ class PAMAlphabet:
         return out
 
 
+def F_Z(z, mu, sigma):
+    z = _f64(z)
+    out = np.zeros(z.size)
+    lib().qro_F_Z(_p(z, _dp), z.size, float(mu), float(sigma), _p(out, _dp))
+    return out
+
+
 class NoiseMapper:
-    def __init__(self, pa, noise_var, sign_config=None):
+    def __init__(self, pa, noise_var, sign_config=None, trunkation_threshold=1e-21, n_intervals_per_step=1000):
         self.pa = pa
         self.order = pa.order
         self.bit_per_symbol = pa.bit_per_symbol
@@ -122,6 +136,16 @@ class NoiseMapper:
         self.probabilities = pa.probabilities
         sc = np.zeros(pa.order, dtype=np.uint8) if sign_config is None else _u8(sign_config)[:pa.order].copy()
         self.sign_config = sc
+        self.half_order = pa.order >> 1
+        self._sign_g = self._g_signs(sc)
+        # the dense grid of noisemapper.pyx:135-144, built on first use
+        if trunkation_threshold > 1.0:
+            self._y_low, self._y_high = pa.constellation[0] * 10, pa.constellation[-1] * 10
+        else:
+            tmp = np.sqrt(-2.0 * np.log(trunkation_threshold)) * float(np.sqrt(noise_var))
+            self._y_high, self._y_low = pa.constellation[-1] + tmp, pa.constellation[0] - tmp
+        self._n_points = int(np.ceil((self._y_high - self._y_low) * n_intervals_per_step / pa.step)) + 1
+        self._grid = None
         self._h = lib().qro_mapper_create(pa.bit_per_symbol, _p(pa.constellation, _dp),
                                           _p(pa.thresholds, _dp), _p(pa.probabilities, _dp),
                                           self.noise_var, _p(sc, _bp))
@@ -145,6 +169,66 @@ class NoiseMapper:
             lib().qro_mapper_destroy(h)
             self._h = None
 
+    def _g_signs(self, sc):
+        """sign vector g / g_inv work with (the subclasses override it, noisemapper.pyx:775-816)"""
+        return sc
+
+    def _build_grid(self):
+        if self._grid is None:
+            y = np.zeros(self._n_points); F = np.zeros(self._n_points)
+            lib().qro_grid(self._h, float(self._y_low), float(self._y_high), self._n_points, _p(y, _dp), _p(F, _dp))
+            self._grid = (y, F)
+        return self._grid
+
+    @property
+    def y_range(self):
+        return self._build_grid()[0].copy()
+
+    @property
+    def F_Y_values(self):
+        return self._build_grid()[1].copy()
+
+    def F_Y(self, y):
+        y = _f64(y)
+        out = np.zeros(y.size)
+        lib().qro_F_Y(self._h, _p(y, _dp), y.size, _p(out, _dp))
+        return out
+
+    def index_to_val(self, index):
+        return self.constellation[_i64(index)]
+
+    def demap_noise(self, n_hat, symb):
+        n_hat = _f64(n_hat); symb = _i64(symb)
+        if n_hat.size != symb.size:
+            raise ValueError("Sizes do not match")
+        gy, gF = self._build_grid()
+        out = np.zeros(n_hat.size)
+        lib().qro_g_inv(self._h, _p(self._sign_g, _bp), _p(gF, _dp), _p(gy, _dp), gy.size, _p(n_hat, _dp),
+                        _p(symb, _lp), n_hat.size, _p(out, _dp))
+        return out
+
+    def g_inv(self, n_hat, i):
+        return float(self.demap_noise([n_hat], [i])[0])
+
+    def g(self, y, i):
+        return float(self.map_noise([y], [i])[0])
+
+    def _variant(self, fn, n, j):
+        n = _f64(n); j = _i64(j)
+        if n.size != j.size:
+            raise ValueError("Sizes of transformed noise vector and tx symbols do not match")
+        gy, gF = self._build_grid()
+        out = np.zeros(n.size * self.bit_per_symbol)
+        fn(self._h, _p(self._sign_g, _bp), _p(gF, _dp), _p(gy, _dp), gy.size, _p(n, _dp), _p(j, _lp), n.size,
+           _p(out, _dp))
+        return out
+
+    def demap_lappr_simplified_array(self, n, j):
+        return self._variant(lib().qro_demap_simplified, n, j)
+
+    def demap_lappr_sofisticated_array(self, n, j):
+        return self._variant(lib().qro_demap_sofisticated, n, j)
+
     def hard_decide_index(self, y):
         y = _f64(y)
         out = np.zeros(y.size, dtype=np.int64)
@@ -156,7 +240,7 @@ class NoiseMapper:
         if y.size != index.size:
             raise ValueError("Input vectors sizes do not match")
         out = np.zeros(y.size)
-        lib().qro_map_noise(self._h, _p(y, _dp), _p(index, _lp), y.size, _p(out, _dp))
+        lib().qro_map_noise_sign(self._h, _p(self._sign_g, _bp), _p(y, _dp), _p(index, _lp), y.size, _p(out, _dp))
         return out
 
     def g_inv_search(self, n_hat, i, y_accuracy=1e-9):
@@ -174,6 +258,24 @@ class NoiseMapper:
         symb = _i64(symb)
         out = np.zeros(symb.size * self.bit_per_symbol)
         lib().qro_bare_llr(self._h, _p(symb, _lp), symb.size, _p(out, _dp))
+        return out
+
+
+class NoiseMapperFlipSign(NoiseMapper):
+    """noisemapper.pyx:775-797: g / g_inv decreasing on the lower half of the alphabet"""
+
+    def _g_signs(self, sc):
+        out = np.zeros(self.order, dtype=np.uint8)
+        out[: self.half_order] = 1
+        return out
+
+
+class NoiseMapperAntiFlipSign(NoiseMapper):
+    """noisemapper.pyx:798-816: g / g_inv decreasing on the upper half of the alphabet"""
+
+    def _g_signs(self, sc):
+        out = np.zeros(self.order, dtype=np.uint8)
+        out[self.half_order:] = 1
         return out
 
 

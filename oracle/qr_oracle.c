@@ -527,3 +527,145 @@ QRO_API void qro_decode_frames(const qro_decoder *d, const double *llr, const ui
         success[f] = (uint8_t)qro_decode(d, llr + f * d->N, synd + f * d->C, max_iterations,
                                          post + f * d->N, iters + f);
 }
+
+/* ------------------------------------------------------------------------- */
+/* Rest of the NoiseMapper surface                 */
+
+/* F_Z -- noisemapper.pyx:70-80.                                              */
+QRO_API void qro_F_Z(const double *z, long n, double mu, double sigma, double *out)
+{
+    for (long i = 0; i < n; ++i) out[i] = gauss_cdf(z[i], mu, sigma);
+}
+
+/* NoiseMapper.F_Y -- noisemapper.pyx:264-275: UNIFORM weights (sum / order), */
+/* not the alphabet's probabilities; summed i = 0 upward, divided last.       */
+QRO_API void qro_F_Y(const qro_mapper *m, const double *y, long n, double *out)
+{
+    for (long j = 0; j < n; ++j) {
+        double res = gauss_cdf(y[j], m->constellation[0], m->sigma);
+        for (int i = 1; i < m->order; ++i) res += gauss_cdf(y[j], m->constellation[i], m->sigma);
+        out[j] = res / m->order;
+    }
+}
+
+/* the dense grid of noisemapper.pyx:135-144: numpy.linspace(low, high, n) is  */
+/* arange(n) * step + low with the last point set to `high`; F_Y on it.        */
+QRO_API void qro_grid(const qro_mapper *m, double y_low, double y_high, long n, double *y, double *F)
+{
+    const double step = (y_high - y_low) / (double)(n - 1);
+    for (long i = 0; i < n; ++i) {
+        volatile double t = (double)i * step;   /* two roundings, as numpy does */
+        y[i] = t + y_low;
+    }
+    if (n > 1) y[n - 1] = y_high;
+    qro_F_Y(m, y, n, F);
+}
+
+/* __interp -- noisemapper.pyx:47-63.                                         */
+QRO_API double qro_interp(const double *dom, const double *cod, long n, double val)
+{
+    if (val >= dom[n - 1]) return cod[n - 1];
+    long index = region_search(dom, n, val);
+    if (index == n - 1) return cod[index];
+    if (dom[index + 1] == dom[index]) return cod[index];
+    volatile double num = (cod[index + 1] - cod[index]) * (val - dom[index]);
+    return cod[index] + num / (dom[index + 1] - dom[index]);
+}
+
+/* g_inv -- noisemapper.pyx:295-307 (and the subclasses' :786-797, :805-816 through `sign`:      */
+/* sign[i] != 0 selects the decreasing branch).  demap_noise -- :391-404.                          */
+QRO_API void qro_g_inv(const qro_mapper *m, const uint8_t *sign, const double *gridF, const double *gridY,
+                       long npts, const double *n_hat, const long *idx, long n, double *out)
+{
+    for (long j = 0; j < n; ++j) {
+        const long i = idx[j];
+        volatile double prod = n_hat[j] * m->delta_F_Y[i];
+        const double target = sign[i] ? m->F_Y_thresholds[i + 1] - prod : prod + m->F_Y_thresholds[i];
+        out[j] = qro_interp(gridF, gridY, npts, target);
+    }
+}
+
+/* g with an explicit sign vector (NoiseMapper.g :289-292, FlipSign :776-780, AntiFlipSign :799-802) */
+QRO_API void qro_map_noise_sign(const qro_mapper *m, const uint8_t *sign, const double *y, const long *idx,
+                                long n, double *out)
+{
+    for (long j = 0; j < n; ++j) {
+        long i = idx[j];
+        double F = mixture_cdf(m, y[j]);
+        out[j] = sign[i] ? (m->F_Y_thresholds[i + 1] - F) / m->delta_F_Y[i]
+                         : (F - m->F_Y_thresholds[i]) / m->delta_F_Y[i];
+    }
+}
+
+/* demap_lappr_simplified(_array) -- noisemapper.pyx:563-621 ("formulation 1").                    */
+QRO_API void qro_demap_simplified(const qro_mapper *m, const uint8_t *sign, const double *gridF,
+                                  const double *gridY, long npts, const double *n_hat, const long *tx,
+                                  long n, double *lappr)
+{
+    const double two_s2 = 2 * m->noise_var;
+    for (long s = 0; s < n; ++s) {
+        double N[16], D[16];
+        const double a_j = m->constellation[tx[s]];
+        for (int k = 0; k < m->bps; ++k) { N[k] = 0; D[k] = 0; }
+        for (long i = 0; i < m->order; ++i) {
+            double yh;
+            qro_g_inv(m, sign, gridF, gridY, npts, &n_hat[s], &i, 1, &yh);
+            volatile double sq = (yh - a_j) * (yh - a_j);
+            const double e = exp(-sq / two_s2);
+            long q = i;
+            for (int k = 0; k < m->bps; ++k) {
+                if ((q * (q + 1)) & 3) D[k] += e;
+                else N[k] += e;
+                q >>= 1;
+            }
+        }
+        for (int k = 0; k < m->bps; ++k) lappr[s * m->bps + k] = log(N[k]) - log(D[k]);
+    }
+}
+
+/* demap_lappr_sofisticated(_array) -- noisemapper.pyx:624-766 ("formulation 3"), as written:      */
+/* every hypothetical sample is g_inv(n, j) (j, not i: :656-657), the exponent is divided by        */
+/* 2 sigma^2 in both branches (:666-675), A_i = beta_i S - dF_i B (:733).                           */
+QRO_API void qro_demap_sofisticated(const qro_mapper *m, const uint8_t *sign, const double *gridF,
+                                    const double *gridY, long npts, const double *n_hat, const long *tx,
+                                    long n, double *lappr)
+{
+    const int M = m->order;
+    const double two_s2 = 2 * m->noise_var, sqrt2sigma = sqrt(two_s2);
+    const double *a = m->constellation, *p = m->probabilities;
+    for (long s = 0; s < n; ++s) {
+        const long j = tx[s];
+        const double a_j = a[j];
+        double yh, beta[256], dFZ[256], N[16], D[16], S = 0, B = 0;
+        qro_g_inv(m, sign, gridF, gridY, npts, &n_hat[s], &j, 1, &yh);
+        for (int i = 0; i < M; ++i) {
+            double e = p[j];
+            for (long q = 0; q < j; ++q) {
+                volatile double pr = (2 * yh - a[q] - a_j) * (a[q] - a_j);
+                volatile double t = p[q] * exp(pr / two_s2);
+                e += t;
+            }
+            for (long q = j + 1; q < M; ++q) {
+                volatile double pr = (2 * yh - a[q] - a[j]) * (a[q] - a_j);
+                volatile double t = p[q] * exp(pr / two_s2);
+                e += t;
+            }
+            beta[i] = m->delta_F_Y[i] / e;
+            B += beta[i];
+            dFZ[i] = 0.5 * (erf((yh - a_j) / sqrt2sigma) - m->inf_erf_table[i * M + j]);
+            S += dFZ[i];
+        }
+        for (int k = 0; k < m->bps; ++k) { N[k] = 0; D[k] = 0; }
+        for (int i = 0; i < M; ++i) {
+            volatile double t1 = beta[i] * S, t2 = dFZ[i] * B;
+            const double A = t1 - t2;
+            long q = i;
+            for (int k = 0; k < m->bps; ++k) {
+                if ((q * (q + 1)) & 3) D[k] += A;
+                else N[k] += A;
+                q >>= 1;
+            }
+        }
+        for (int k = 0; k < m->bps; ++k) lappr[s * m->bps + k] = log(N[k]) - log(D[k]);
+    }
+}

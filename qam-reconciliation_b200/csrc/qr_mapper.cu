@@ -17,7 +17,7 @@ static MapperView view_of(const qr_mapper *m)
     v.order = m->order; v.bps = m->bps;
     v.noise_var = m->noise_var; v.sigma = m->sigma; v.s2 = m->s2;
     v.constellation = m->constellation; v.thresholds = m->thresholds; v.probabilities = m->probabilities;
-    v.sign_config = m->d_sign; v.FY_thr = m->FY_thr; v.delta = m->delta; v.bare = m->bare;
+    v.sign_config = m->d_sign; v.sign_g = m->d_sign_g; v.FY_thr = m->FY_thr; v.delta = m->delta; v.bare = m->bare;
     v.inv_tab = m->inv_tab; v.inv_pdf = m->inv_pdf; v.inv_n = m->inv_n; v.inv_y0 = m->inv_y0; v.inv_h = m->inv_h;
     return v;
 }
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_front_end(MapperView m, const double *_
         if (idx_out) idx_out[j] = i;
         if (n_hat) {
             const double F = mixture_cdf(s.a, s.p, m.order, m.s2, y[j]);
-            n_hat[j] = s.sign[i] ? add_rn(s.FYt[i + 1], -F) / s.delta[i] : add_rn(F, -s.FYt[i]) / s.delta[i];
+            n_hat[j] = m.sign_g[i] ? add_rn(s.FYt[i + 1], -F) / s.delta[i] : add_rn(F, -s.FYt[i]) / s.delta[i];
         }
         if (bits) {
             for (int k = 0; k < m.bps; ++k) bits[j * m.bps + k] = gray_bit(i, k);
@@ -192,6 +192,7 @@ int qr_mapper_create(int bits_per_symbol, const double *h_constellation, const d
         m->n_table_doubles = nd;
         QR_CUDA_CHECK(cudaMalloc((void **)&m->d_tables, nd * sizeof(double)));
         QR_CUDA_CHECK(cudaMalloc((void **)&m->d_sign, M));
+        QR_CUDA_CHECK(cudaMalloc((void **)&m->d_sign_g, M));
         double *p = m->d_tables;
         m->constellation = p; p += M;
         m->thresholds = p; p += M + 1;
@@ -207,6 +208,7 @@ int qr_mapper_create(int bits_per_symbol, const double *h_constellation, const d
         QR_CUDA_CHECK(cudaMemcpy(m->probabilities, h_probabilities, M * sizeof(double), cudaMemcpyHostToDevice));
         if (h_sign_config) QR_CUDA_CHECK(cudaMemcpy(m->d_sign, h_sign_config, M, cudaMemcpyHostToDevice));
         else QR_CUDA_CHECK(cudaMemset(m->d_sign, 0, M));
+        QR_CUDA_CHECK(cudaMemcpy(m->d_sign_g, m->d_sign, M, cudaMemcpyDeviceToDevice));
         qr::k_mapper_tables<<<1, 32>>>(qr::view_of(m), m->FY_thr, m->delta, m->fwrd, m->back, m->bare, m->inf_erf);
         QR_CUDA_CHECK(cudaGetLastError());
         // inverse-CDF starting table: +-9 sigma around the constellation, ~2e-3 sigma-free grid step
@@ -237,6 +239,8 @@ void qr_mapper_destroy(qr_mapper *m)
         qr::DeviceGuard guard(m->device);
         cudaFree(m->d_tables);
         cudaFree(m->d_sign);
+        cudaFree(m->d_sign_g);
+        cudaFree(m->grid_y);
         cudaFree(m->inv_tab);
     }
     delete m;

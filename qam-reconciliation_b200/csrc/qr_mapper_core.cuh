@@ -20,7 +20,8 @@ struct MapperView {
     const double *constellation;  // [order]
     const double *thresholds;     // [order+1]
     const double *probabilities;  // [order]
-    const uint8_t *sign_config;   // [order]
+    const uint8_t *sign_config;   // [order]   ctor sign_config: g_inv_search / demap_lappr
+    const uint8_t *sign_g;        // [order]   sign rule of g / map_noise (== sign_config except for the FlipSign subclasses)
     const double *FY_thr;         // [order+1]  F_Y_thresholds
     const double *delta;          // [order]    delta_F_Y
     const double *bare;           // [order*bps]

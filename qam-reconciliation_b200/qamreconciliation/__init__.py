@@ -6,7 +6,8 @@ There is no CPU fallback: constructing any compute class without a CUDA device r
 """
 from .decoder import Decoder
 from .matrix import Matrix
-from .noisemapper import NoiseMapper, NoiseDemapper
+from .noisemapper import NoiseMapper, NoiseDemapper, NoiseMapperFlipSign, NoiseMapperAntiFlipSign
 from .alphabet import PAMAlphabet
 
-__all__ = ["Decoder", "Matrix", "NoiseMapper", "NoiseDemapper", "PAMAlphabet"]
+__all__ = ["Decoder", "Matrix", "NoiseMapper", "NoiseDemapper", "NoiseMapperFlipSign", "NoiseMapperAntiFlipSign",
+           "PAMAlphabet"]

@@ -50,6 +50,13 @@ SIGNATURES = {
     "qr_g_inv_search": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp]),
     "qr_bare_llr": (C.c_int, [_vp, _vp, _i64, _vp, C.c_int, _vp]),
     "qr_direct_llr": (C.c_int, [_vp, _vp, _i64, _f64, _vp, C.c_int, _vp]),
+    "qr_mapper_set_g_sign": (C.c_int, [_vp, _vp]),
+    "qr_mapper_build_grid": (C.c_int, [_vp, _f64, _f64, _i64]),
+    "qr_mapper_grid": (C.c_int, [_vp, _P(_i64), _vp, _vp]),
+    "qr_F_Y": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "qr_F_Z": (C.c_int, [_vp, _i64, _f64, _f64, _vp, _vp]),
+    "qr_demap_noise": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "qr_demap_lappr_variant": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp, _vp]),
     "qr_reconcile_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f64, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp,
                                       C.c_int, _vp, _vp, _vp, _vp]),
     "qr_reconcile_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f64, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp,

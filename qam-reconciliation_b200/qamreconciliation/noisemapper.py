@@ -86,6 +86,10 @@ class NoiseMapper:
             h, self.F_Y_thresholds.ctypes.data, self.delta_F_Y.ctypes.data,
             self.fwrd_transition_probability.ctypes.data, self.back_transition_probability.ctypes.data,
             self.bare_llr_table.ctypes.data, self.inf_erf_table.ctypes.data))
+        sg = self._g_signs()
+        if sg is not None:
+            sg = np.ascontiguousarray(sg, dtype=np.uint8)
+            _abi.check(_abi.lib().qr_mapper_set_g_sign(h, sg.ctypes.data))
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -96,11 +100,17 @@ class NoiseMapper:
                 pass
             self._h = None
 
-    # -- lazily built grid (noisemapper.pyx:135-144, :254-261) ------------------------------------
+    # -- sign rule of g / g_inv (overridden by the FlipSign subclasses, noisemapper.pyx:775-816) ------
+    def _g_signs(self):
+        return None
+
+    # -- lazily built grid (noisemapper.pyx:135-144, :254-261), computed and kept on the device ------
     def _build_grid(self):
         if self._grid is None:
-            y = np.linspace(self._y_low, self._y_high, self._n_points)
-            self._grid = (y, self.F_Y(y))
+            _abi.check(_abi.lib().qr_mapper_build_grid(self._h, float(self._y_low), float(self._y_high), self._n_points))
+            y = np.empty(self._n_points); F = np.empty(self._n_points)
+            _abi.check(_abi.lib().qr_mapper_grid(self._h, None, y.ctypes.data, F.ctypes.data))
+            self._grid = (y, F)
         return self._grid
 
     @property
@@ -111,15 +121,66 @@ class NoiseMapper:
     def F_Y_values(self):
         return np.array(self._build_grid()[1])
 
-    def F_Y(self, y):
-        """noisemapper.pyx:264-275: (sum of the Gaussian CDFs) / order, on the GPU via torch.erf."""
+    def F_Y_batch(self, y):
         t = to_dev(y, torch.float64)
-        a = torch.as_tensor(self.constellation, dtype=torch.float64, device=t.device)
-        s2 = math.sqrt(2) * self.noise_sigma
-        res = 0.5 * (1 + torch.erf((t - a[0]) / s2))
-        for i in range(1, self.order):
-            res = res + 0.5 * (1 + torch.erf((t - a[i]) / s2))
-        return to_np(res / self.order)
+        out = torch.empty(t.shape, dtype=torch.float64, device=t.device)
+        _abi.check(_abi.lib().qr_F_Y(self._h, t.data_ptr(), t.numel(), out.data_ptr(), stream()))
+        return out
+
+    def F_Y(self, y):
+        """noisemapper.pyx:264-275: (sum of the Gaussian CDFs) / order"""
+        return to_np(self.F_Y_batch(to_dev(y, torch.float64).reshape(-1)))
+
+    def demap_noise_batch(self, n_hat, symb):
+        """g_inv per element: interpolation on the F_Y grid (noisemapper.pyx:391-404, :295-307, :47-63)"""
+        nn = to_dev(n_hat, torch.float64); ss = to_dev(symb, torch.int64)
+        if nn.numel() != ss.numel():
+            raise ValueError("Sizes do not match")
+        self._build_grid()
+        out = torch.empty(nn.shape, dtype=torch.float64, device=nn.device)
+        _abi.check(_abi.lib().qr_demap_noise(self._h, nn.data_ptr(), ss.data_ptr(), nn.numel(), out.data_ptr(), stream()))
+        return out
+
+    def demap_noise(self, n_hat, symb):
+        """noisemapper.pyx:391-404"""
+        return to_np(self.demap_noise_batch(to_dev(n_hat, torch.float64).reshape(-1),
+                                            to_dev(symb, torch.int64).reshape(-1)))
+
+    def g_inv(self, n_hat, i):
+        """noisemapper.pyx:295-307"""
+        return float(self.demap_noise(np.array([float(n_hat)]), np.array([int(i)], dtype=np.int64))[0])
+
+    def _variant_batch(self, variant, n, j):
+        nn = to_dev(n, torch.float64); jj = to_dev(j, torch.int64)
+        if nn.numel() != jj.numel():
+            raise ValueError("Sizes of transformed noise vector and tx symbols do not match")
+        self._build_grid()
+        out = torch.empty(nn.shape[:-1] + (nn.shape[-1] * self.bit_per_symbol,), dtype=torch.float64, device=nn.device)
+        _abi.check(_abi.lib().qr_demap_lappr_variant(self._h, variant, nn.data_ptr(), jj.data_ptr(), nn.numel(),
+                                                     out.data_ptr(), stream()))
+        return out
+
+    def demap_lappr_simplified_array_batch(self, n, j):
+        return self._variant_batch(1, n, j)
+
+    def demap_lappr_sofisticated_array_batch(self, n, j):
+        return self._variant_batch(2, n, j)
+
+    def demap_lappr_simplified_array(self, n, j):
+        """noisemapper.pyx:605-621"""
+        return to_np(self._variant_batch(1, to_dev(n, torch.float64).reshape(-1), to_dev(j, torch.int64).reshape(-1)))
+
+    def demap_lappr_simplified(self, n, j):
+        """noisemapper.pyx:563-601"""
+        return self.demap_lappr_simplified_array(np.array([float(n)]), np.array([int(j)], dtype=np.int64))
+
+    def demap_lappr_sofisticated_array(self, n, j):
+        """noisemapper.pyx:751-766"""
+        return to_np(self._variant_batch(2, to_dev(n, torch.float64).reshape(-1), to_dev(j, torch.int64).reshape(-1)))
+
+    def demap_lappr_sofisticated(self, n, j):
+        """noisemapper.pyx:624-748"""
+        return self.demap_lappr_sofisticated_array(np.array([float(n)]), np.array([int(j)], dtype=np.int64))
 
     # -- hot path, batched ---------------------------------------------------------------------------
     def hard_decide_index_batch(self, y_samples):
@@ -237,3 +298,30 @@ class NoiseMapper:
 class NoiseDemapper(NoiseMapper):
     """Empty subclass, as in the reference (noisemapper.pxd:89-92)."""
     pass
+
+
+class NoiseMapperFlipSign(NoiseMapper):
+    """noisemapper.pyx:775-797: g / g_inv decreasing on the lower half of the alphabet.  As in the reference,
+    g_inv_search / demap_lappr are NOT overridden and keep the constructor's sign_config."""
+
+    def _g_signs(self):
+        sg = np.zeros(self.order, dtype=np.uint8)
+        sg[: self.half_order] = 1
+        return sg
+
+
+class NoiseMapperAntiFlipSign(NoiseMapper):
+    """noisemapper.pyx:798-816: g / g_inv decreasing on the upper half of the alphabet."""
+
+    def _g_signs(self):
+        sg = np.zeros(self.order, dtype=np.uint8)
+        sg[self.half_order:] = 1
+        return sg
+
+
+def F_Z(z, mu, sigma):
+    """module function F_Z (noisemapper.pyx:70-80)"""
+    t = to_dev(z, torch.float64).reshape(-1)
+    out = torch.empty(t.shape, dtype=torch.float64, device=t.device)
+    _abi.check(_abi.lib().qr_F_Z(t.data_ptr(), t.numel(), float(mu), float(sigma), out.data_ptr(), stream()))
+    return to_np(out)

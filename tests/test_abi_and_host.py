@@ -17,7 +17,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 def header_symbols():
     text = open(os.path.join(ROOT, "include", "qamrecon.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(qr_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(qr_[A-Za-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():
