@@ -185,6 +185,15 @@ int qr_demap_noise(const qr_mapper *m, const double *d_n_hat, const int64_t *d_s
 int qr_demap_lappr_variant(const qr_mapper *m, int variant, const double *d_n_hat, const int64_t *d_tx_index,
                            int64_t n, double *d_llr, void *stream);
 
+/* mutual_information.montecarlo_information (mutual_information.pyx:212-300) after its sample draw: for the
+ * samples (x_ind[n] Alice's symbols, y[n] Bob's channel outputs, device arrays) ADDS to d_sums[3] the sums over
+ * the samples of the three per-sample terms -- log2(P(xhat)/P(xhat|x)) (:257-258), log2 of the I(X;Y) kernel
+ * (:262-268), and minus log2 of the I(X,N;Xhat) kernel (:272-290); the caller zeroes d_sums and divides by n
+ * (:293-295).  which: bit 0/1/2 selects the term (the reference's `which` array); d_p_Xhat[order] = P_xhat(nm)
+ * (:29-39); demap_mode: QR_DEMAP_EXACT or QR_DEMAP_FAST for the one g_inv_search per sample (:280). */
+int qr_information_sums(const qr_mapper *m, const double *d_p_Xhat, const int64_t *d_x_ind, const double *d_y,
+                        int64_t n, int which, int demap_mode, double *d_sums, void *stream);
+
 /* ---------------------------------------------------------------- whole path, device buffers
  * The chain of sims/reconciliation.pyx:129-153 (mode 0 soft reverse, 1 hard reverse :300-308,
  * 2 soft direct :214-227) for `frames` frames whose channel outputs d_y [frames][S] and Alice's

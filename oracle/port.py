@@ -43,6 +43,7 @@ def lib():
         L.qro_map_noise_sign.argtypes = [C.c_void_p, _bp, _dp, _lp, C.c_long, _dp]
         L.qro_demap_simplified.argtypes = [C.c_void_p, _bp, _dp, _dp, C.c_long, _dp, _lp, C.c_long, _dp]
         L.qro_demap_sofisticated.argtypes = [C.c_void_p, _bp, _dp, _dp, C.c_long, _dp, _lp, C.c_long, _dp]
+        L.qro_information.argtypes = [C.c_void_p, _bp, _dp, _dp, C.c_long, _dp, _lp, _dp, C.c_long, _bp, _dp]
         L.qro_gray_table.argtypes = [C.c_int, _bp]
         L.qro_alphabet.argtypes = [C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp]
         L.qro_hard_decide_index.argtypes = [_dp, C.c_int, _dp, C.c_long, _lp]
@@ -277,6 +278,22 @@ class NoiseMapperAntiFlipSign(NoiseMapper):
         out = np.zeros(self.order, dtype=np.uint8)
         out[self.half_order:] = 1
         return out
+
+
+def P_xhat(nm):
+    """mutual_information.pyx:29-39"""
+    return np.array([sum(nm.probabilities[j] * nm.fwrd_transition_probability[j, i] for j in range(nm.order))
+                     for i in range(nm.order)])
+
+
+def information_from_samples(nm, p_Xhat, x_ind, y, which=(1, 1, 1)):
+    """mutual_information.pyx:241-298 for given samples -> (I_X_Xhat, I_X_Y, I_XN_Xhat)"""
+    x_ind = _i64(x_ind); y = _f64(y); p_Xhat = _f64(p_Xhat); which = _u8(which)
+    gy, gF = nm._build_grid()
+    out = np.zeros(3)
+    lib().qro_information(nm._h, _p(nm._sign_g, _bp), _p(gF, _dp), _p(gy, _dp), gy.size, _p(p_Xhat, _dp),
+                          _p(x_ind, _lp), _p(y, _dp), y.size, _p(which, _bp), _p(out, _dp))
+    return tuple(out)
 
 
 def direct_llr(y, pa, two_variance):

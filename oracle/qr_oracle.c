@@ -669,3 +669,68 @@ QRO_API void qro_demap_sofisticated(const qro_mapper *m, const uint8_t *sign, co
         for (int k = 0; k < m->bps; ++k) lappr[s * m->bps + k] = log(N[k]) - log(D[k]);
     }
 }
+
+/* ------------------------------------------------------------------------- */
+/* Mutual-information Monte Carlo                  */
+/* montecarlo_information -- mutual_information.pyx:212-300, for GIVEN         */
+/* samples (x_ind, y): the reference draws them with numpy's global RNG       */
+/* (:236-239); everything after the draw is restated here, accumulated in     */
+/* sample order and divided by N last (:293-295).  which[3] as at :217.       */
+static double mi_inner(const qro_mapper *m, double yh, long xi)
+{
+    const double *a = m->constellation, *p = m->probabilities;
+    const double x = a[xi], two_s2 = 2.0 * m->noise_var;
+    double tmp = p[xi];
+    for (long q = 0; q < m->order; ++q) {
+        if (q == xi) continue;
+        volatile double pr = (2 * yh - x - a[q]) * (a[q] - x);
+        volatile double t = p[q] * exp(pr / two_s2);
+        tmp += t;
+    }
+    return tmp;
+}
+
+QRO_API void qro_information(const qro_mapper *m, const uint8_t *sign_g, const double *gridF,
+                             const double *gridY, long npts, const double *p_Xhat, const long *x_ind,
+                             const double *y, long N, const uint8_t *which, double *out3)
+{
+    const int M = m->order;
+    const double *a = m->constellation, *p = m->probabilities;
+    const double two_s2 = 2.0 * m->noise_var;
+    double I0 = 0, I1 = 0, I2 = 0;
+    for (long s = 0; s < N; ++s) {
+        const long xi = x_ind[s];
+        long xh = region_search(m->thresholds, M + 1, y[s]);
+        if (xh == M) xh = M - 1;
+        double nv;
+        qro_map_noise_sign(m, sign_g, &y[s], &xh, 1, &nv);
+        const double x = a[xi];
+        if (which[0]) I0 += log2(p_Xhat[xh] / m->fwrd[xi * M + xh]);
+        if (which[1]) {
+            double tmp = p[xi];
+            for (long k = 0; k < M; ++k) {
+                if (k == xi) continue;
+                volatile double pr = (2 * y[s] - a[k] - x) * (a[k] - x);
+                volatile double t = p[k] * exp(pr / two_s2);
+                tmp += t;
+            }
+            I1 += log2(tmp);
+        }
+        if (which[2]) {
+            double acc = 0;
+            for (long k = 0; k < M; ++k) {
+                if (k == xh) continue;
+                double yh;
+                qro_g_inv(m, sign_g, gridF, gridY, npts, &nv, &k, 1, &yh);
+                acc += m->delta_F_Y[k] / mi_inner(m, yh, xi);
+            }
+            const double yh = qro_g_inv_search(m, nv, (int)xh, 1e-9);
+            volatile double r = mi_inner(m, yh, xi) / m->delta_F_Y[xh];
+            acc *= r;
+            acc += 1;
+            acc *= p_Xhat[xh];
+            I2 -= log2(acc);
+        }
+    }
+    out3[0] = I0 / N; out3[1] = I1 / N; out3[2] = I2 / N;
+}

@@ -147,6 +147,87 @@ __global__ void __launch_bounds__(128) k_demap_variant(MapperView m, const uint8
     }
 }
 
+// ---- mutual-information Monte Carlo: the per-sample terms of
+// montecarlo_information (mutual_information.pyx:241-298) for given samples (x_ind, y), summed.
+// T(y_hat) = p_x + sum_{m != x} p_m exp((2 y_hat - a_x - a_m)(a_m - a_x) / 2 sigma^2)   (:274-277, :281-284)
+__device__ __forceinline__ double mi_inner(const SharedTables &s, int M, double two_s2, double yh, int32_t xi)
+{
+    const double x = s.a[xi];
+    double tmp = s.p[xi];
+    for (int q = 0; q < M; ++q) {
+        if (q == xi) continue;
+        const double pr = mul_rn(add_rn(add_rn(mul_rn(2, yh), -x), -s.a[q]), add_rn(s.a[q], -x));
+        tmp = add_rn(tmp, mul_rn(s.p[q], exp(pr / two_s2)));
+    }
+    return tmp;
+}
+
+__global__ void __launch_bounds__(128) k_information(MapperView m, const uint8_t *__restrict__ sign_g,
+                                                     const double *__restrict__ gF, const double *__restrict__ gy,
+                                                     int32_t npts, const double *__restrict__ fwrd,
+                                                     const double *__restrict__ p_Xhat,
+                                                     const long long *__restrict__ x_ind,
+                                                     const double *__restrict__ y, int64_t n, int which, int mode,
+                                                     double *__restrict__ sums)
+{
+    __shared__ SharedTables s;
+    __shared__ uint8_t sg[kMaxOrder];
+    __shared__ double red[3][4];
+    stage_tables(m, s);
+    for (int i = threadIdx.x; i < m.order; i += blockDim.x) sg[i] = sign_g[i];
+    __syncthreads();
+    const int M = m.order;
+    const double two_s2 = 2.0 * m.noise_var;
+    double I0 = 0, I1 = 0, I2 = 0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t xi = (int32_t)x_ind[j];
+        const double yv = y[j], x = s.a[xi];
+        const int32_t xh = hard_decide(s.thr, M, yv);                                   // :241
+        const double F = mixture_cdf(s.a, s.p, M, m.s2, yv);                            // :242 (g)
+        const double nv = sg[xh] ? add_rn(s.FYt[xh + 1], -F) / s.delta[xh] : add_rn(F, -s.FYt[xh]) / s.delta[xh];
+        if (which & 1) I0 += log2(p_Xhat[xh] / fwrd[xi * M + xh]);                      // :257-258
+        if (which & 2) {                                                                // :262-268
+            double tmp = s.p[xi];
+            for (int k = 0; k < M; ++k) {
+                if (k == xi) continue;
+                const double pr = mul_rn(add_rn(add_rn(mul_rn(2, yv), -s.a[k]), -x), add_rn(s.a[k], -x));
+                tmp = add_rn(tmp, mul_rn(s.p[k], exp(pr / two_s2)));
+            }
+            I1 += log2(tmp);
+        }
+        if (which & 4) {                                                                // :272-290
+            double acc = 0;
+            for (int k = 0; k < M; ++k) {
+                if (k == xh) continue;
+                const double yh = g_inv_grid(s, sg, gF, gy, npts, nv, k);
+                acc = add_rn(acc, s.delta[k] / mi_inner(s, M, two_s2, yh, xi));
+            }
+            const double target = inv_target(s.sign, s.FYt, s.delta, nv, xh);
+            const double yh = (mode & 1) ? g_inv_fast(s.a, s.p, s.thr, s.FYt, M, m.sigma, m.s2, target, 1e-9, xh,
+                                                      InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h})
+                                         : g_inv_exact(s.a, s.p, M, m.s2, target, 1e-9);
+            acc = mul_rn(acc, mi_inner(s, M, two_s2, yh, xi) / s.delta[xh]);
+            acc = add_rn(acc, 1.0);
+            acc = mul_rn(acc, p_Xhat[xh]);
+            I2 -= log2(acc);
+        }
+    }
+    // block reduction, then one atomic per block and term
+    for (int o = 16; o > 0; o >>= 1) {
+        I0 += __shfl_down_sync(0xffffffffu, I0, o);
+        I1 += __shfl_down_sync(0xffffffffu, I1, o);
+        I2 += __shfl_down_sync(0xffffffffu, I2, o);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][w] = I0; red[1][w] = I1; red[2][w] = I2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[threadIdx.x][i];
+        atomicAdd(&sums[threadIdx.x], t);
+    }
+}
+
 static unsigned grid_for(int64_t n, int per_block)
 {
     int64_t g = (n + per_block - 1) / per_block;
@@ -251,6 +332,23 @@ int qr_demap_lappr_variant(const qr_mapper *m, int variant, const double *d_n_ha
     else
         qr::k_demap_variant<2><<<qr::grid_for(n, 128), 128, 0, st>>>(qr::mapper_view(m), m->d_sign_g, m->grid_F, m->grid_y,
                                                                       m->grid_n, m->inf_erf, d_n_hat, tx, n, d_llr);
+    QR_CUDA_CHECK(cudaGetLastError());
+    return QR_OK;
+}
+
+int qr_information_sums(const qr_mapper *m, const double *d_p_Xhat, const int64_t *d_x_ind, const double *d_y,
+                        int64_t n, int which, int demap_mode, double *d_sums, void *stream)
+{
+    if (!m) return qr::fail(QR_ERR_INVALID, "null mapper");
+    if (n < 0) return qr::fail(QR_ERR_INVALID, "negative length");
+    if (which < 0 || which > 7) return qr::fail(QR_ERR_INVALID, "which is a 3-bit mask");
+    if ((which & 4) && !m->grid_n) return qr::fail(QR_ERR_INVALID, "F_Y grid not built (qr_mapper_build_grid)");
+    if (n == 0) return QR_OK;
+    if (!d_p_Xhat || !d_x_ind || !d_y || !d_sums) return qr::fail(QR_ERR_INVALID, "null array");
+    qr::DeviceGuard guard(m->device);
+    qr::k_information<<<qr::grid_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        qr::mapper_view(m), m->d_sign_g, m->grid_F, m->grid_y, m->grid_n, m->fwrd, d_p_Xhat,
+        reinterpret_cast<const long long *>(d_x_ind), d_y, n, which, demap_mode, d_sums);
     QR_CUDA_CHECK(cudaGetLastError());
     return QR_OK;
 }

@@ -57,6 +57,7 @@ SIGNATURES = {
     "qr_F_Z": (C.c_int, [_vp, _i64, _f64, _f64, _vp, _vp]),
     "qr_demap_noise": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "qr_demap_lappr_variant": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp, _vp]),
+    "qr_information_sums": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp]),
     "qr_reconcile_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f64, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp,
                                       C.c_int, _vp, _vp, _vp, _vp]),
     "qr_reconcile_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f64, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp,
