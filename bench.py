@@ -367,12 +367,14 @@ def ours(a):
     peak, peak_src = peaks()
     achieved = fi * bytes_per_frame_iter / (k_ms / 1e3) / 1e9
     traffic = None
-    try:   # DRAM bytes of the same launch from the committed ncu --set full capture (profiles/)
+    try:   # DRAM bytes of the same launch from the committed ncu --set full captures (profiles/)
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        c = tj["config"]
-        if (c["n"], c["frames"], c["max_iterations"], c["precision"]) == (n, B, MAXITER, a.precision) and \
-                a.schedule == 0 and fi == B * MAXITER:
-            traffic = tj["dram_bytes_per_launch"]
+        for ent in tj.get("entries", [tj]):
+            c = ent["config"]
+            sched = {"persistent": 0, "launch": 1, "fused": 2}[c["schedule"]]
+            if (c["n"], c["frames"], c["max_iterations"], c["precision"], sched, c["lanes"]) == \
+                    (n, B, MAXITER, a.precision, a.schedule, a.lanes or 512) and fi == B * MAXITER:
+                traffic = ent["dram_bytes_per_launch"]
     except Exception:
         pass
     kname = {0: "k_persistent (decoder, one launch per batch)", 1: "k_check+k_var",
