@@ -526,6 +526,7 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
         if (const char *v = getenv("QAMRECON_FUSED_PIPE")) d->fused_pipe = atoi(v);
         if (const char *v = getenv("QAMRECON_FUSED_PREFETCH")) d->fused_prefetch = atoi(v);
         if (const char *v = getenv("QAMRECON_FUSED_RPC")) d->fused_rpc = atoi(v);
+        if (const char *v = getenv("QAMRECON_FUSED_STATIC")) d->fused_static = atoi(v);
         const size_t L = (size_t)lanes;
         QR_CUDA_CHECK(cudaMalloc(&d->c2v, (size_t)g->E * L * w));
         QR_CUDA_CHECK(cudaMalloc(&d->post, (size_t)g->N * L * w));

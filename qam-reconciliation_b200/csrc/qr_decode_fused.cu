@@ -78,42 +78,59 @@ __device__ __forceinline__ void prefetch_next_tile(const FusedParams<T> &F, int 
     (void)c0; (void)c1;
 }
 
+// Work distribution: WARPS claim work, not CTAs.  A warp is 32 / bx checks wide (bx = TL / VEC threads share a
+// check) and takes rows_per_claim passes per claim from one global counter, in tile order; the atomic of the
+// NEXT claim is issued before the current one is processed.  No CTA barrier inside the phase, so the warps of
+// an SM drift apart and cover each other's memory round trips (measured: a CTA-wide claim with its barrier cost
+// 2.1 us per claim, profiles/r1_fused_experiments.txt f7/f8).  Per-lane "some check unsatisfied" flags are
+// OR-reduced inside the warp and stored per tile (idempotent stores of 1).
 template <typename T, int VEC, int DSEL>
 __device__ __forceinline__ void fused_phase(const FusedParams<T> &F, int cur, int32_t *s_flags, int32_t *s_claim,
                                             uint64_t pol_ld, uint64_t pol_st)
 {
+    (void)s_flags; (void)s_claim;
     const DecodeParams<T> &P = F.P;
-    const int32_t bx = F.tl / VEC, by = kFBlock / bx;
-    const int32_t tx = threadIdx.x % bx, ty = threadIdx.x / bx;
-    const int32_t claim_rows = by * F.rows_per_claim, C = (int32_t)P.C;
+    const int32_t bx = F.tl / VEC;                    // threads per check row (<= 32)
+    const int32_t lane = threadIdx.x & 31;
+    const int32_t tx = lane % bx, tyw = lane / bx, wy = 32 / bx;
+    const int32_t claim_rows = wy * F.rows_per_claim, C = (int32_t)P.C;
     const int32_t cpt = (C + claim_rows - 1) / claim_rows, total = cpt * F.tiles;
     int32_t tile_prev = -1;
     uint32_t bad = 0;
     LaneInfo<VEC> L;
     L.active = 0;
     TileView<T> V;
-    // claims are fetched one ahead: the atomic of the NEXT claim is in flight while this one is processed, and
-    // the two-entry mailbox needs a single CTA barrier per claim
-    if (threadIdx.x == 0) s_claim[0] = atomicAdd(&P.work[0], 1);
-    __syncthreads();
-    for (int32_t it = 0;; ++it) {
-        const int32_t cl = s_claim[it & 1];
-        if (threadIdx.x == 0 && cl < total) s_claim[(it + 1) & 1] = atomicAdd(&P.work[0], 1);
-        const int32_t tile = cl < total ? cl / cpt : -1;
-        if (tile != tile_prev) {
-            if (tile_prev >= 0) flush_bad<VEC>(P.unsat[cur], tile_prev * F.tl, tx, ty, F.tl, bad, s_flags);
-            bad = 0;
+    auto flush = [&]() {
+        uint32_t b = bad;
+        for (int32_t o = bx; o < 32; o <<= 1) b |= __shfl_xor_sync(0xffffffffu, b, o);
+        if (tyw == 0) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                if (b >> k & 1) P.unsat[cur][tile_prev * F.tl + tx * VEC + k] = 1;
         }
-        if (tile < 0) break;    // (also the CTAs that never got a claim: tile_prev == -1)
+        bad = 0;
+    };
+    // static_share (per mille) of the claims of a step is dealt round-robin to the warps without any atomic
+    // (claims gw, gw + W, ...); the rest is claimed dynamically so that a slow SM does not hold the barrier
+    const int32_t W = (int32_t)(gridDim.x * (kFBlock / 32)), gw = (int32_t)(blockIdx.x * (kFBlock / 32) + (threadIdx.x >> 5));
+    const int32_t n_static = (int32_t)((int64_t)total * F.static_share / 1000) / W * W;
+    int32_t nxt = gw < n_static ? gw : -1;
+    if (nxt < 0) {
+        if (lane == 0) nxt = n_static + atomicAdd(&P.work[0], 1);
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+    for (;;) {
+        const int32_t cl = nxt;
+        if (cl >= total) break;
+        const bool dyn = cl + W >= n_static;                   // the next claim comes from the counter
+        if (!dyn) nxt = cl + W;
+        else if (lane == 0) nxt = n_static + atomicAdd(&P.work[0], 1);   // in flight while this claim is processed
+        const int32_t tile = cl / cpt;
         if (tile != tile_prev) {
+            if (tile_prev >= 0) flush();
             L = load_lane_info<T, VEC>(P, cur, (tile * F.tl) / VEC + tx);
             V = tile_view(F, cur, tile);
             tile_prev = tile;
-        }
-        {
-            const int32_t c0 = (cl - tile * cpt) * claim_rows, c1 = min(c0 + claim_rows, C);
-            if (F.prefetch && P.n_bins == 1)   // (check-regular graphs: the claim's CSR slots are one contiguous range)
-                prefetch_next_tile<T>(F, cur, tile, cl - tile * cpt, cpt, c0, c1, c0 * P.bins[0].degree, c1 * P.bins[0].degree);
         }
         if (L.active) {
             const int32_t c0 = (cl - tile * cpt) * claim_rows, c1 = min(c0 + claim_rows, C);
@@ -122,12 +139,13 @@ __device__ __forceinline__ void fused_phase(const FusedParams<T> &F, int cur, in
                 const int32_t lo = max(c0, bin.chk_begin), hi = min(c1, bin.chk_begin + bin.count);
                 if (lo >= hi) continue;
                 const CheckBin sub{bin.degree, lo, hi - lo, bin.slot_begin + (lo - bin.chk_begin) * bin.degree};
-                if constexpr (DSEL > 0) bad |= run_fused_bin<T, VEC, DSEL>(V, F.nbr, L, tx * VEC, sub, ty, by, pol_ld, pol_st);
-                else bad |= run_fused_bin_any<T, VEC>(V, F.nbr, L, tx * VEC, sub, ty, by, pol_ld, pol_st);
+                if constexpr (DSEL > 0) bad |= run_fused_bin<T, VEC, DSEL>(V, F.nbr, L, tx * VEC, sub, tyw, wy, pol_ld, pol_st);
+                else bad |= run_fused_bin_any<T, VEC>(V, F.nbr, L, tx * VEC, sub, tyw, wy, pol_ld, pol_st);
             }
         }
-        __syncthreads();
+        if (dyn) nxt = __shfl_sync(0xffffffffu, nxt, 0);
     }
+    if (tile_prev >= 0) flush();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -198,7 +216,7 @@ __device__ __forceinline__ void fused_phase_pipe(const FusedParams<T> &F, int cu
                     L_active = L.active; L_fresh = L.fresh;
                     cl_tile = tile;
                 }
-                if (F.prefetch) {
+                if (F.prefetch & 1) {
                     // The gathers of a tile touch its rows in random order; left to them, the first touch of
                     // every row is a random 128..256-byte DRAM access (row-buffer miss each time).  Instead the
                     // SAME chunk of the NEXT tile is pulled into L2 here in address order, one claim ahead of
@@ -687,12 +705,13 @@ int run_batch_fused(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream
     F.c2v[1] = static_cast<T *>(d->c2v2);
     int32_t tl = d->fused_tile > 0 ? d->fused_tile : 32;
     tl = std::min<int32_t>(tl, kFusedMaxTile);
-    while (tl > 32 && (P.lanes % tl || (tl / VEC) > kFBlock)) tl /= 2;
+    while (tl > 32 && (P.lanes % tl || (tl / VEC) > 32)) tl /= 2;   // a check row is shared by at most one warp
     F.tl = tl;
     F.tiles = P.lanes / tl;
     F.hints = d->fused_hints;
     F.prefetch = d->fused_prefetch;
     F.rows_per_claim = d->fused_rpc > 0 ? d->fused_rpc : 4;
+    F.static_share = d->fused_static;
 #ifdef QR_FUSED_EXPERIMENTS
     // staging variants measured on B200 and found slower than the register-staged phase:
     // 1 / 2 = per-thread cp.async stages, 3 = TMA bulk copies of whole rows

@@ -49,8 +49,9 @@ struct FusedParams {
     int32_t tl;          // lanes per tile
     int32_t tiles;
     int32_t hints;       // L2 policy: 0 none, 1 stores evict-first, 2 + loads evict-last
+    int32_t static_share;     // per mille of a step's claims dealt statically (no atomic), the rest is work-stolen
     int32_t rows_per_claim;   // checks per thread and work-stealing claim (register-staged phase)
-    int32_t prefetch;    // 1: stream the next tile into L2 in address order, one claim ahead of the sweep
+    int32_t prefetch;    // bit 0: stream the next tile into L2 in address order, one claim ahead of the sweep; bit 1: next item
 };
 
 // ---- 16-byte row accesses with an L2 policy (device) / plain (host emulation)
@@ -94,6 +95,7 @@ struct TileView {
     const T *llr;
     const uint8_t *synd;
     int32_t tl;
+    int32_t item_prefetch;   // pull the rows of the thread group's next item into L2 (FusedParams::prefetch bit 1)
 };
 
 template <typename T>
@@ -101,6 +103,7 @@ QR_HD TileView<T> tile_view(const FusedParams<T> &F, int cur, int32_t tile)
 {
     TileView<T> V;
     V.tl = F.tl;
+    V.item_prefetch = (F.prefetch >> 1) & 1;
     V.c_old = F.c2v[cur] + (int64_t)tile * F.P.E * F.tl;
     V.c_new = F.c2v[cur ^ 1] + (int64_t)tile * F.P.E * F.tl;
     V.llr = F.P.llr + (int64_t)tile * F.P.N * F.tl;
@@ -196,8 +199,23 @@ QR_HD uint32_t run_fused_bin(const TileView<T> &V, const Nbr4 *nbr, const LaneIn
 {
     uint32_t bad = 0;
     if constexpr (FUSED_HALF_BATCH != 0) {
-        // register-lean variant: no index prefetch (latency is covered by the second resident CTA)
+        // register-lean variant: no index prefetch into registers (latency is covered by the second resident
+        // CTA).  Instead the rows of the thread group's NEXT item are pulled into L2 while this one is
+        // processed: the bx threads of a group split the 4 D row ids of the next neighbour record row among
+        // themselves (ids read straight from the table, L1), one prefetch.global.L2 each -- no register is
+        // held, and the demand loads of the next item find their compulsory DRAM misses already in L2.
         for (int32_t k = first; k < bin.count; k += stride) {
+#if defined(__CUDA_ARCH__)
+            if (V.item_prefetch && k + stride < bin.count) {
+                const int32_t *raw = reinterpret_cast<const int32_t *>(nbr + bin.slot_begin + (k + stride) * D);
+                const int32_t bx = V.tl / VEC, tx = lt / VEC;
+                for (int32_t r = tx; r < 4 * D; r += bx) {
+                    const int32_t id = __ldg(raw + r);
+                    const T *row = (r & 3) == 0 ? V.llr + (int64_t)(id & 0x0fffffff) * V.tl : V.c_old + (int64_t)id * V.tl;
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(row));
+                }
+            }
+#endif
             Nbr4 cur[D];
             load_nbr_row<D>(nbr, bin.slot_begin + k * D, cur);
             // steady state (no lane of the thread on its first half-iteration): no per-element selects

@@ -140,7 +140,7 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     P.ctrl = ctrl.data(); P.stats = stats; P.work = nullptr; P.refill_list = nullptr;
     F.nbr = reinterpret_cast<const Nbr4 *>(g.slot_nbr.data());
     F.c2v[0] = c2v0.data(); F.c2v[1] = c2v1.data();
-    F.tl = tl; F.tiles = lanes / tl; F.hints = 0; F.prefetch = 0; F.rows_per_claim = 2;
+    F.tl = tl; F.tiles = lanes / tl; F.hints = 0; F.prefetch = 0; F.rows_per_claim = 2; F.static_share = 0;
     for (int l = 0; l < lanes; ++l) {
         LaneState s;
         s.frame = l < frames ? l : -1; s.iter = 0; s.fresh = s.frame >= 0; s.retire = -1;

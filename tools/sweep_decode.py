@@ -66,6 +66,7 @@ def main():
             if combo:
                 parts = (combo.split(":") + ["0", "0", "2"])[:5] if combo.count(":") < 4 else combo.split(":")
                 os.environ["QAMRECON_FUSED_RPC"] = parts[4]
+                os.environ["QAMRECON_FUSED_STATIC"] = parts[5] if len(parts) > 5 else "0"
                 os.environ["QAMRECON_FUSED_PREFETCH"] = parts[3]
                 os.environ["QAMRECON_FUSED_TILE"], os.environ["QAMRECON_FUSED_HINTS"] = parts[0], parts[1]
                 os.environ["QAMRECON_FUSED_PIPE"] = parts[2]
