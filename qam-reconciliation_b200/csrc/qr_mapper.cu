@@ -19,6 +19,7 @@ static MapperView view_of(const qr_mapper *m)
     v.constellation = m->constellation; v.thresholds = m->thresholds; v.probabilities = m->probabilities;
     v.sign_config = m->d_sign; v.sign_g = m->d_sign_g; v.FY_thr = m->FY_thr; v.delta = m->delta; v.bare = m->bare;
     v.inv_tab = m->inv_tab; v.inv_pdf = m->inv_pdf; v.inv_n = m->inv_n; v.inv_y0 = m->inv_y0; v.inv_h = m->inv_h;
+    v.inv_jump = m->inv_jump; v.inv_jn = m->inv_jn;
     return v;
 }
 
@@ -70,6 +71,20 @@ __global__ void k_fill_inv_table(MapperView m, double *tab, double *pdf, int32_t
         tab[j] = mixture_cdf(m.constellation, m.probabilities, m.order, m.s2, y0 + j * h);
         pdf[j] = mixture_pdf(m.constellation, m.probabilities, m.order, m.sigma, y0 + j * h);
     }
+}
+
+// jump[t] = largest grid index g with tab[g] <= t / jn (0 if none): see InvTable::jump
+__global__ void k_fill_jump_table(const double *__restrict__ tab, int32_t n, int32_t *__restrict__ jump, int32_t jn)
+{
+    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > jn) return;
+    const double v = (double)t / (double)jn;
+    int32_t lo = 0, hi = n;           // invariant: tab[lo] <= v (or lo == 0), tab[hi] > v (or hi == n)
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (tab[mid] <= v) lo = mid; else hi = mid;
+    }
+    jump[t] = lo;
 }
 
 // hard decision (+ softening metric) (+ Gray bits) in one pass over y
@@ -124,7 +139,7 @@ __global__ void __launch_bounds__(128) k_g_inv(MapperView m, const double *__res
          j += (int64_t)gridDim.x * blockDim.x) {
         const int32_t i = (int32_t)region[j];
         const double target = inv_target(s.sign, s.FYt, s.delta, n_hat[j], i);
-        y_hat[j] = (mode & 1) ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i, InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h})
+        y_hat[j] = (mode & 1) ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i, InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h, m.inv_jump, m.inv_jn})
                               : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
     }
 }
@@ -223,6 +238,10 @@ int qr_mapper_create(int bits_per_symbol, const double *h_constellation, const d
             qr::k_fill_inv_table<<<(m->inv_n + 255) / 256, 256>>>(v, m->inv_tab, m->inv_pdf, m->inv_n, m->inv_y0, m->inv_h);
         }
         QR_CUDA_CHECK(cudaGetLastError());
+        m->inv_jn = 8192;
+        QR_CUDA_CHECK(cudaMalloc((void **)&m->inv_jump, (size_t)(m->inv_jn + 2) * sizeof(int32_t)));
+        qr::k_fill_jump_table<<<(m->inv_jn + 1 + 255) / 256, 256>>>(m->inv_tab, m->inv_n, m->inv_jump, m->inv_jn);
+        QR_CUDA_CHECK(cudaGetLastError());
         QR_CUDA_CHECK(cudaDeviceSynchronize());
         return QR_OK;
     };
@@ -242,6 +261,7 @@ void qr_mapper_destroy(qr_mapper *m)
         cudaFree(m->d_sign_g);
         cudaFree(m->grid_y);
         cudaFree(m->inv_tab);
+        cudaFree(m->inv_jump);
     }
     delete m;
 }

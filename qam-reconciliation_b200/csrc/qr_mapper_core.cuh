@@ -30,6 +30,8 @@ struct MapperView {
     const double *inv_pdf;
     int32_t inv_n;
     double inv_y0, inv_h;
+    const int32_t *inv_jump;      // see InvTable::jump
+    int32_t inv_jn;
 };
 
 struct InvTable {
@@ -37,6 +39,10 @@ struct InvTable {
     const double *f;   // its density at the same points (may be NULL: no Hermite solve)
     int32_t n;
     double y0, h;
+    // optional: jump[t] = largest grid index g with F[g] <= t / jn (t = 0..jn, jn a power of two): narrows the
+    // search for a target to the few grid cells of its bin instead of a binary search over the whole region
+    const int32_t *jump = nullptr;
+    int32_t jn = 0;
 };
 
 // rounding-exact multiply/add: the reference is compiled without FMA contraction
@@ -234,6 +240,12 @@ QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, con
             const int32_t g = (int32_t)((thr[region + 1] - tab.y0) / tab.h) + 2;
             if (g > lo && g < hi && tab.F[g] > target) hi = g;
         }
+        if (tab.jump) {
+            const int32_t t = (int32_t)(target * tab.jn);       // exact: jn is a power of two
+            const int32_t g0 = tab.jump[t], g1 = tab.jump[t + 1] + 1;
+            if (g0 > lo) lo = g0;                               // F[g0] <= t / jn <= target
+            if (g1 < hi) hi = g1;                               // F[g1] > (t + 1) / jn > target
+        }
         while (hi - lo > 1) {
             const int32_t mid = (lo + hi) >> 1;
             if (tab.F[mid] <= target) lo = mid; else hi = mid;
@@ -351,6 +363,22 @@ QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, con
     // there the reference's answer is set by the rounding of F, not by the root.  Replay it exactly.
     if (!(f * accuracy > 1e-14)) return g_inv_exact(a, p, order, s2, target, accuracy);
     // replay of noisemapper.pyx:319-344 against the root
+    if (accuracy == 1e-9 && fabs(root) < 4.0e6) {
+        // Default accuracy, closed form.  The bracket [lo, hi] the doubling loop leaves has a power-of-two width
+        // W = 2^e and ends that are multiples of it; 2^-30 <= 1e-9 < 2^-29, so the halving loop always stops at
+        // cells of width exactly 2^-30 aligned at 0, whatever e, and returns the midpoint of the cell with
+        // lo_cell <= root < hi_cell:  (floor(root * 2^30) + 1/2) * 2^-30  (all operations exact in double).
+        // One exception: a root that IS the upper end of the bracket (target > 1/2 and root a power of two >= 1:
+        // the doubling loop stops at hi == root) belongs to the last cell of the bracket, the one below it.
+        double q = floor(root * 0x1p30);
+        if (target > .5 && root >= 1.0) {
+            int ex = 0;
+            if (frexp(root, &ex) == 0.5) q -= 1.0;
+        }
+        if (target > .5 && root <= 0.0) q = 0.0;                    // bracket [0, 1]: roots below it go to its first cell
+        if (!(target > .5) && root >= 0.0) q = -1.0;                // bracket [-1, 0]: roots above it go to its last cell
+        return (q + 0.5) * 0x1p-30;
+    }
     double lo, hi;
     if (target > .5) {
         hi = 1; lo = 0;
@@ -439,23 +467,26 @@ QR_HD void demap_symbol(const MapperView &m, const TablesRef &s, double nv, int3
 {
     const bool fast = (mode & 1) != 0, corrected = (mode & QR_DEMAP_CORRECTED) != 0;
     const double two_s2 = 2 * m.noise_var;
+    // fast mode (tolerance 1e-7): multiply by the reciprocal instead of dividing twelve times
+    // per symbol, one log of the ratio instead of two logs; exact mode keeps the reference's operations
+    const double inv_two_s2 = 1.0 / two_s2;
     double N[kMaxBps], D[kMaxBps];
     for (int k = 0; k < m.bps; ++k) { N[k] = 0; D[k] = 0; }
     for (int i = 0; i < m.order; ++i) {
         const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
         const double yh = fast ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i,
-                                            InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h})
+                                            InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h, m.inv_jump, m.inv_jn})
                                : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
         double sum = 0;
         for (int k = 0; k < j; ++k) {
             double ex = mul_rn(add_rn(add_rn(mul_rn(2, yh), -s.a[k]), -s.a[j]), add_rn(s.a[k], -s.a[j]));
-            if (corrected) ex = ex / two_s2;
+            if (corrected) ex = fast ? ex * inv_two_s2 : ex / two_s2;
             sum = add_rn(sum, mul_rn(exp(ex), s.p[k]));
         }
         sum = add_rn(sum, s.p[j]);
         for (int k = j + 1; k < m.order; ++k) {
-            const double ex =
-                mul_rn(add_rn(add_rn(mul_rn(2, yh), -s.a[k]), -s.a[j]), add_rn(s.a[k], -s.a[j])) / two_s2;
+            const double pr = mul_rn(add_rn(add_rn(mul_rn(2, yh), -s.a[k]), -s.a[j]), add_rn(s.a[k], -s.a[j]));
+            const double ex = fast ? pr * inv_two_s2 : pr / two_s2;
             sum = add_rn(sum, mul_rn(exp(ex), s.p[k]));
         }
         const double w = s.delta[i] / sum;
@@ -467,7 +498,7 @@ QR_HD void demap_symbol(const MapperView &m, const TablesRef &s, double nv, int3
         }
     }
     for (int k = 0; k < m.bps; ++k) {
-        double v = log(N[k]) - log(D[k]);
+        double v = fast ? log(N[k] / D[k]) : log(N[k]) - log(D[k]);
         if (alpha != 1.0) v = mul_rn(v, alpha);
         out[k] = v;
     }

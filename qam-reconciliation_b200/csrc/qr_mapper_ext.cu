@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(128) k_information(MapperView m, const uint8_t
             }
             const double target = inv_target(s.sign, s.FYt, s.delta, nv, xh);
             const double yh = (mode & 1) ? g_inv_fast(s.a, s.p, s.thr, s.FYt, M, m.sigma, m.s2, target, 1e-9, xh,
-                                                      InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h})
+                                                      InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h, m.inv_jump, m.inv_jn})
                                          : g_inv_exact(s.a, s.p, M, m.s2, target, 1e-9);
             acc = mul_rn(acc, mi_inner(s, M, two_s2, yh, xi) / s.delta[xh]);
             acc = add_rn(acc, 1.0);

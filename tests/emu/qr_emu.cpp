@@ -255,7 +255,20 @@ void emu_demap(int bps, const double *a, const double *thr, const double *p, dou
         tabf[j] = mixture_pdf(a, p, M, sigma, ty0 + j * th);
     }
     // mode bit 2: no table at all; bit 3: table of F only (no Hermite solve)
-    const InvTable tab{(mode & 4) ? nullptr : tabF.data(), (mode & 12) ? nullptr : tabf.data(), (mode & 4) ? 0 : tn, ty0, th};
+    const int32_t jn = 8192;
+    std::vector<int32_t> jump(jn + 2, 0);
+    for (int32_t t = 0; t <= jn; ++t) {
+        const double v = (double)t / (double)jn;
+        int32_t lo = 0, hi = tn;
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (tabF[mid] <= v) lo = mid; else hi = mid;
+        }
+        jump[t] = lo;
+    }
+    // mode bit 4: without the jump table (plain binary search over the region)
+    const InvTable tab{(mode & 4) ? nullptr : tabF.data(), (mode & 12) ? nullptr : tabf.data(), (mode & 4) ? 0 : tn, ty0, th,
+                       (mode & 16) ? nullptr : jump.data(), (mode & 16) ? 0 : jn};
     for (int64_t s = 0; s < n; ++s) {
         for (int i = 0; i < M; ++i) {
             const double target = inv_target(sign, FYt.data(), delta.data(), n_hat[s], i);

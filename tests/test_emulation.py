@@ -255,6 +255,9 @@ def test_emulated_mapper_against_reference(path):
         # mode bit 3: F table as a starting point only (Halley polish instead of the Hermite solve)
         L.emu_demap(bps, ptr(a), ptr(thr), ptr(p), nv, ptr(sc), ptr(nn), ptr(jj), C.c_int64(nn.size), 9, ptr(fast2), ptr(yh_f2))
         assert np.max(np.abs(yh_f2 - yh_e)) <= 1.1e-9 and np.mean(yh_f2 == yh_e) > 0.98
+        # mode bit 4 (16): without the jump table that narrows the grid search -- identical results
+        L.emu_demap(bps, ptr(a), ptr(thr), ptr(p), nv, ptr(sc), ptr(nn), ptr(jj), C.c_int64(nn.size), 17, ptr(fast2), ptr(yh_f2))
+        assert np.array_equal(yh_f2, yh_f) and np.array_equal(fast2, fast)
         np.testing.assert_allclose(exact, g[lk], rtol=1e-9, atol=1e-9)
         # the fast inverse lands in the same 1e-9 cell as the bisection (a neighbouring one at worst)
         assert np.max(np.abs(yh_f - yh_e)) <= 1.1e-9
