@@ -52,16 +52,16 @@ def parse():
                     help="frames resident in the decoder (0 = library default; -1 = 1024 for the fused schedule, else 0)")
     ap.add_argument("--schedule", type=int, default=-1,
                     help="0 persistent two-phase kernel, 1 launch per phase, 2 fused flooding iteration (persistent); "
-                         "-1 = 2 in fp32, 0 in fp64")
+                         "-1 = 2")
     ap.add_argument("--n", type=int, default=N_CODE, help="code length (default: the metric's 64800)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames per CPU worker (0 = auto)")
     a = ap.parse_args()
     if a.schedule < 0:
-        a.schedule = 2 if a.precision == "fp32" else 0
+        a.schedule = 2
     if a.lanes < 0:
-        a.lanes = 1024 if a.schedule == 2 else 0
+        a.lanes = (1024 if a.precision == "fp32" else 512) if a.schedule == 2 else 0
     return a
 
 
