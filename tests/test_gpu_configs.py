@@ -148,3 +148,45 @@ def test_config5_hard_reverse_and_direct_modes(env, mode):
     assert [int(v) for v in out["iters"].cpu()] == [w[1] for w in want]
     assert np.array_equal(out["word"].cpu().numpy(), np.array([w[3] for w in want]))
     np.testing.assert_allclose(out["post"].cpu().numpy(), np.array([w[2] for w in want]), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("schedule", [0, 2])
+def test_config2_full_size_properties_and_schedule_agreement(env, schedule):
+    """BASELINE config 2 at its full size, n = 64 800 (3,6)-regular, 4-PAM Alternating, above the waterfall:
+    size-independent properties (round trip to Bob's word, truthful flags, idempotence), and the fused and
+    two-phase schedules agreeing frame by frame -- bit for bit in fp64, decisions in fp32."""
+    qr, codes, _ = env
+    from qamreconciliation.pipeline import Reconciler
+    n, bps = 64800, 2
+    vid, cid = codes.regular_ldpc(n, 3, 6, seed=1)
+    dec = qr.Decoder(vid, cid); pa = qr.PAMAlphabet(bps, 2)
+    n0 = pa.variance * 10 ** (-4.6 / 10) / 2
+    nm = qr.NoiseMapper(pa, n0, np.array([0, 1, 0, 1], dtype=np.uint8))
+    gen = torch.Generator(device="cuda"); gen.manual_seed(11)
+    frames = 160                                    # more frames than lanes: continuous batching in play
+    x = torch.randint(0, 4, (frames, n // bps), device="cuda", generator=gen)
+    y = torch.tensor(pa.constellation, device="cuda")[x] + float(np.sqrt(n0)) * torch.randn(
+        x.shape, device="cuda", dtype=torch.float64, generator=gen)
+    out = Reconciler(dec, nm, precision="fp32", demap="fast", lanes=64, schedule=schedule).run_device(y, x, 50, k_info=n // 2)
+    ok = out["success"].bool()
+    assert ok.float().mean() > 0.95
+    assert torch.equal((out["post"] < 0).to(torch.uint8)[ok], out["word"][ok])
+    assert torch.equal(dec.check_lappr_batch(out["post"], out["synd"]).bool(), ok)
+    assert (out["bit_errors"][ok] == 0).all()
+    it = out["iters"]
+    assert len(set(it.tolist())) > 3 and int(it[ok].max()) < 50
+    ok2, it2, _ = dec.decode_batch(out["post"][ok], out["synd"][ok], 50, precision="fp32", schedule=schedule)
+    assert ok2.all() and (it2 == 0).all()
+    if schedule == 2:
+        # the same LLRs through both schedules
+        idx, nh, word = nm.front_end_batch(y[:48])
+        synd = qr.Matrix(vid, cid).eval_syndrome_batch(word)
+        llr = nm.demap_lappr_array_batch(nh, x[:48], mode="fast")
+        a = dec.decode_batch(llr, synd, 50, precision="fp64", lanes=32, schedule=0)
+        b = dec.decode_batch(llr, synd, 50, precision="fp64", lanes=32, schedule=2)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        assert torch.equal(a[2].view(torch.int64), b[2].view(torch.int64))          # bit-identical posteriors
+        a32 = dec.decode_batch(llr.float(), synd, 50, precision="fp32", lanes=32, schedule=0)
+        b32 = dec.decode_batch(llr.float(), synd, 50, precision="fp32", lanes=32, schedule=2)
+        assert torch.equal(a32[0], b32[0]) and (a32[1] - b32[1]).abs().max() <= 1
+        assert torch.equal(a32[2] < 0, b32[2] < 0)
