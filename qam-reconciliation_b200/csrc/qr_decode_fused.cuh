@@ -127,7 +127,11 @@ QR_HD uint32_t fused_item(const TileView<T> &V, const LaneInfo<VEC> &L, int32_t 
     VT x[D];
     // the 4 D row loads go out in batches of HB edges (HB = D: all at once; smaller: fewer registers held
     // by loads in flight, so two CTAs fit an SM)
+#ifdef FUSED_BATCH_EDGES
+    constexpr int HB = FUSED_BATCH_EDGES < D ? FUSED_BATCH_EDGES : D;
+#else
     constexpr int HB = (FUSED_HALF_BATCH && D > 3) ? (D + 1) / 2 : D;
+#endif
 #pragma unroll
     for (int i0 = 0; i0 < D; i0 += HB) {
         VT m[HB][3], ch[HB];
