@@ -355,6 +355,7 @@ __global__ void k_init_batch(LaneState *st0, LaneState *st1, int32_t *unsat0, in
         ctrl[CTRL_REFILL_CNT + 0] = (int32_t)min((int64_t)lanes, frames);
         ctrl[CTRL_REFILL_CNT + 1] = 0;
         ctrl[6] = 0;   // CTRL_ARRIVE of the fused schedule
+        ctrl[7] = 0x7fffffff; ctrl[8] = 0x7fffffff;   // CTRL_MINFIN, CTRL_MINFIN_NEXT
         stats[0] = 0;
         stats[1] = 0;
     }
@@ -527,6 +528,7 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
         if (const char *v = getenv("QAMRECON_FUSED_PREFETCH")) d->fused_prefetch = atoi(v);
         if (const char *v = getenv("QAMRECON_FUSED_RPC")) d->fused_rpc = atoi(v);
         if (const char *v = getenv("QAMRECON_FUSED_STATIC")) d->fused_static = atoi(v);
+        if (const char *v = getenv("QAMRECON_FUSED_STORE_POST")) d->fused_store_post = atoi(v);
         const size_t L = (size_t)lanes;
         QR_CUDA_CHECK(cudaMalloc(&d->c2v, (size_t)g->E * L * w));
         QR_CUDA_CHECK(cudaMalloc(&d->post, (size_t)g->N * L * w));
@@ -538,6 +540,8 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
         QR_CUDA_CHECK(cudaMalloc((void **)&d->stats, 2 * sizeof(unsigned long long)));
         QR_CUDA_CHECK(cudaMalloc((void **)&d->work, 2 * qr::kMaxLaneTiles * sizeof(int32_t)));
         QR_CUDA_CHECK(cudaMalloc((void **)&d->refill_list, 2 * L * sizeof(int32_t)));
+        QR_CUDA_CHECK(cudaMalloc((void **)&d->postok, 2 * L * sizeof(int32_t)));
+        QR_CUDA_CHECK(cudaMemset(d->postok, 0, 2 * L * sizeof(int32_t)));
         QR_CUDA_CHECK(cudaMemset(d->c2v, 0, (size_t)g->E * L * w));
         QR_CUDA_CHECK(cudaMemset(d->post, 0, (size_t)g->N * L * w));
         QR_CUDA_CHECK(cudaMemset(d->llr, 0, (size_t)g->N * L * w));
@@ -562,7 +566,7 @@ void qr_decoder_destroy(qr_decoder *d)
     cudaGetDevice(&prev);
     cudaSetDevice(d->device);
     cudaFree(d->c2v); cudaFree(d->c2v2); cudaFree(d->post); cudaFree(d->llr); cudaFree(d->synd);
-    cudaFree(d->st); cudaFree(d->unsat); cudaFree(d->ctrl); cudaFree(d->stats); cudaFree(d->work); cudaFree(d->refill_list);
+    cudaFree(d->st); cudaFree(d->unsat); cudaFree(d->ctrl); cudaFree(d->stats); cudaFree(d->work); cudaFree(d->refill_list); cudaFree(d->postok);
     cudaFree(d->pipe_buf);
     cudaFree(d->dev_buf);
     if (d->pipe_streams_ready) {

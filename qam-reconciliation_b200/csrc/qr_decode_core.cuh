@@ -54,7 +54,7 @@ struct LaneState {
 // CTRL_FIN_STEP: index of the last step in which a frame finished (so a refill phase is due)
 // CTRL_REFILL_CNT[2]: lanes listed for the refill phase, double-buffered like the lane state
 enum : int { CTRL_NEXT_FRAME = 0, CTRL_REMAINING = 1, CTRL_SNAPSHOT = 2, CTRL_FIN_STEP = 3, CTRL_REFILL_CNT = 4,
-             CTRL_WORDS = 8 };
+             CTRL_WORDS = 16 };
 constexpr int kMaxLaneTiles = 1 << 15;
 
 template <typename T>
@@ -332,6 +332,7 @@ struct LaneInfo {
     uint32_t fresh;   // bit k: no variable update yet for this frame: its c2v column counts as zero
     // variable phase decisions
     uint32_t fin_ok, fin_fail, upd;
+    uint32_t wpost;   // fused schedule: lanes whose posterior is stored this step (they may finish in it)
 };
 
 template <typename T, int VEC>
@@ -339,7 +340,7 @@ QR_HD LaneInfo<VEC> load_lane_info(const DecodeParams<T> &P, int cur, int32_t jv
 {
     LaneInfo<VEC> L;
     L.l0 = jv * VEC;
-    L.active = L.fresh = L.fin_ok = L.fin_fail = L.upd = 0;
+    L.active = L.fresh = L.fin_ok = L.fin_fail = L.upd = L.wpost = 0;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
         const LaneState s = ld_stream(&P.st[cur][L.l0 + k]);

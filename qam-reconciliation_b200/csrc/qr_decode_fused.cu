@@ -104,6 +104,7 @@ __device__ __forceinline__ void fused_phase(const FusedParams<T> &F, int cur, in
     LaneInfo<VEC> L;
     L.active = 0;
     TileView<T> V;
+    const int32_t minfin = ld_stream(&P.ctrl[CTRL_MINFIN]);   // fixed for the whole phase (updated between phases)
     auto flush = [&]() {
         uint32_t b = bad;
         for (int32_t o = bx; o < 32; o <<= 1) b |= __shfl_xor_sync(0xffffffffu, b, o);
@@ -133,6 +134,7 @@ __device__ __forceinline__ void fused_phase(const FusedParams<T> &F, int cur, in
         if (tile != tile_prev) {
             if (tile_prev >= 0) flush();
             L = load_lane_info<T, VEC>(P, cur, (tile * F.tl) / VEC + tx);
+            mark_post_lanes<T, VEC>(F, L, minfin);
             V = tile_view(F, cur, tile);
             tile_prev = tile;
         }
@@ -557,7 +559,22 @@ __device__ __forceinline__ void fused_refill_phase(const FusedParams<T> &F, int 
         }
         const int32_t n0 = r * span + threadIdx.x;
         T *llr_col = P.llr + (int64_t)tile * P.N * tl + lt;
-        if (s.retire >= 0 && P.post_out) {
+        const bool post_valid = F.post && s.retire >= 0 && ld_stream(&F.postok[(int64_t)buf * P.lanes + lane]) != 0;
+        if (s.retire >= 0 && P.post_out && post_valid && ld_stream(&P.iters[s.retire]) != 0) {
+            // the phase stored this frame's posteriors: one column of N elements
+            const T *pc = F.post + (int64_t)tile * P.N * tl + lt;
+            T v[kFRefillRows];
+#pragma unroll
+            for (int i = 0; i < kFRefillRows; ++i) {
+                const int32_t n = n0 + i * kFBlock;
+                if (n < P.N) v[i] = ld_stream(&pc[(int64_t)n * tl]);
+            }
+#pragma unroll
+            for (int i = 0; i < kFRefillRows; ++i) {
+                const int32_t n = n0 + i * kFBlock;
+                if (n < P.N) store_output_llr(P.post_out, P.post_out_f64, (int64_t)s.retire * P.N + n, (double)v[i]);
+            }
+        } else if (s.retire >= 0 && P.post_out) {
             if (ld_stream(&P.iters[s.retire]) == 0) {
                 LaneState only_retire = s;
                 only_retire.frame = -1;
@@ -653,11 +670,15 @@ __global__ void __launch_bounds__(kFBlock, (PIPE == 1 || (PIPE == 3 && sizeof(T)
                 atomicAdd(&P.stats[1], 1ULL);
             }
             __syncthreads();
+            const int32_t minfin = ld_stream(&P.ctrl[CTRL_MINFIN]);    // what the phase of this step went by
             for (int32_t jv = threadIdx.x; jv < P.lanes / VEC; jv += kFBlock) {
                 LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
                 decide_lanes<T, VEC>(P, cur, L);
+                fused_note_finishers<T, VEC>(F, cur ^ 1, L, minfin);
                 bookkeep_lanes<T, VEC>(P, cur, step, L);
             }
+            __syncthreads();
+            if (threadIdx.x == 0) P.ctrl[CTRL_MINFIN] = *(volatile int32_t *)&P.ctrl[CTRL_MINFIN_NEXT];
         }
         grid.sync();
         if (*(volatile int32_t *)&P.ctrl[CTRL_FIN_STEP] == step) {
@@ -707,6 +728,8 @@ int run_batch_fused(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream
     F.nbr = reinterpret_cast<const Nbr4 *>(g->d_slot_nbr);
     F.c2v[0] = static_cast<T *>(d->c2v);
     F.c2v[1] = static_cast<T *>(d->c2v2);
+    F.post = d->fused_store_post ? static_cast<T *>(d->post) : nullptr;
+    F.postok = d->postok;
     int32_t tl = d->fused_tile > 0 ? d->fused_tile : 32;
     tl = std::min<int32_t>(tl, kFusedMaxTile);
     while (tl > 32 && (P.lanes % tl || (tl / VEC) > 32)) tl /= 2;   // a check row is shared by at most one warp

@@ -39,13 +39,26 @@ struct alignas(16) Nbr4 {
     int32_t n0, n1, n2;  // CSR slots of the variable's edges, ascending edge id
 };
 
-enum : int { CTRL_ARRIVE = 6 };
+// CTRL_MINFIN: smallest iteration count a frame of this batch finished successfully with, as the fused phase of
+// the current step sees it; CTRL_MINFIN_NEXT: the same, being updated by the bookkeeping of the current step
+enum : int { CTRL_ARRIVE = 6, CTRL_MINFIN = 7, CTRL_MINFIN_NEXT = 8 };
+
+// A lane's posterior is STORED (by the check that holds the variable's first edge) in the steps it may finish in:
+// its last allowed iteration, or any iteration from one below the earliest success seen so far in the batch.
+// A frame that finishes in such a step ships from the stored column (N elements); one that finishes earlier than
+// ever seen falls back to rebuilding llr + sum c2v (E + N elements).  Either way the same values.
+QR_HD bool stores_post(int32_t iter, int32_t maxiter, int32_t minfin)
+{
+    return iter >= maxiter || iter >= minfin - 1;
+}
 
 template <typename T>
 struct FusedParams {
     DecodeParams<T> P;   // graph, lane state, batch, control words; P.llr / P.synd are the tile-major arrays
     const Nbr4 *nbr;     // [E]
     T *c2v[2];           // message buffers, step parity selects the one being read
+    T *post;             // [tile][N][TL] posteriors of the lanes that may finish this step (null: always rebuild)
+    int32_t *postok;     // [2][lanes] per state buffer: the retiring frame's posterior column is valid
     int32_t tl;          // lanes per tile
     int32_t tiles;
     int32_t hints;       // L2 policy: 0 none, 1 stores evict-first, 2 + loads evict-last
@@ -94,6 +107,7 @@ struct TileView {
     T *c_new;
     const T *llr;
     const uint8_t *synd;
+    T *post;
     int32_t tl;
     int32_t item_prefetch;   // pull the rows of the thread group's next item into L2 (FusedParams::prefetch bit 1)
 };
@@ -108,7 +122,18 @@ QR_HD TileView<T> tile_view(const FusedParams<T> &F, int cur, int32_t tile)
     V.c_new = F.c2v[cur ^ 1] + (int64_t)tile * F.P.E * F.tl;
     V.llr = F.P.llr + (int64_t)tile * F.P.N * F.tl;
     V.synd = F.P.synd + (int64_t)tile * F.P.C * F.tl;
+    V.post = F.post ? F.post + (int64_t)tile * F.P.N * F.tl : nullptr;
     return V;
+}
+
+template <typename T, int VEC>
+QR_HD void mark_post_lanes(const FusedParams<T> &F, LaneInfo<VEC> &L, int32_t minfin)
+{
+    L.wpost = 0;
+    if (!F.post) return;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+        if ((L.active >> k & 1) && stores_post(L.iter[k], F.P.maxiter, minfin)) L.wpost |= 1u << k;
 }
 
 // FUSED item: internal check `ci` (first CSR slot slot0, degree D) for the thread's VEC lanes at
@@ -150,6 +175,7 @@ QR_HD uint32_t fused_item(const TileView<T> &V, const LaneInfo<VEC> &L, int32_t 
             const int i = i0 + j;
             if (i < D) {
                 const int own = (int)((uint32_t)q[i].vp >> 28);
+                VT pv;
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
                     const bool fresh = ANYFRESH && (L.fresh >> k & 1) != 0;   // first half-iteration: c2v == 0 (decoder.pyx:408)
@@ -159,10 +185,14 @@ QR_HD uint32_t fused_item(const TileView<T> &V, const LaneInfo<VEC> &L, int32_t 
                     T post = ch[j].v[k] + c0;                            // decoder.pyx:291-293, ascending edge id
                     post = post + c1;
                     post = post + c2;
+                    pv.v[k] = post;
                     par ^= (uint32_t)(post < (T)0) << k;                 // decoder.pyx:244 (strict <)
                     const T mine = own == 0 ? c0 : (own == 1 ? c1 : c2);
                     x[i].v[k] = post - mine;                             // decoder.pyx:295-297
                 }
+                // the check holding the variable's FIRST edge keeps the posterior of lanes that may finish now
+                if (L.wpost && own == 0)
+                    *reinterpret_cast<VT *>(V.post + (int64_t)(q[i].vp & 0x0fffffff) * tl + lt) = pv;
             }
         }
     }
@@ -262,7 +292,8 @@ constexpr int kFusedMaxCheckDegree = 8;
 // ---- refill phase, one (lane, variable) element: ship post = llr + sum c2v[cur] of a finished frame
 // (what the two-phase schedule keeps in its post array), bring in the next frame's channel LLR
 template <typename T>
-QR_HD void fused_refill_var_elem(const FusedParams<T> &F, int cur, const LaneState &s, int32_t lane, int32_t n)
+QR_HD void fused_refill_var_elem(const FusedParams<T> &F, int cur, const LaneState &s, int32_t lane, int32_t n,
+                                 bool post_valid = false)
 {
     const DecodeParams<T> &P = F.P;
     const int32_t tile = lane / F.tl, lt = lane % F.tl;
@@ -279,6 +310,8 @@ QR_HD void fused_refill_var_elem(const FusedParams<T> &F, int cur, const LaneSta
                 if (!copied) val = val + 0.0;
                 store_output_llr(P.post_out, P.post_out_f64, idx, val);
             }
+        } else if (post_valid) {
+            store_output_llr(P.post_out, P.post_out_f64, idx, (double)ld_stream(&F.post[at]));
         } else {
             const T *c = F.c2v[cur] + (int64_t)tile * P.E * F.tl + lt;
             T acc = ld_stream(&P.llr[at]);
@@ -288,6 +321,26 @@ QR_HD void fused_refill_var_elem(const FusedParams<T> &F, int cur, const LaneSta
     }
     if (s.frame >= 0 && s.fresh)
         P.llr[at] = load_input_llr<T>(P.llr_in, P.llr_in_f64, (int64_t)s.frame * P.N + n);
+}
+
+// Before bookkeep_lanes of a step: remember, for the lanes that finish in it, whether the phase stored their
+// posterior, and fold their iteration counts into the running minimum.  `nxt` = state buffer being written.
+template <typename T, int VEC>
+QR_HD void fused_note_finishers(const FusedParams<T> &F, int nxt, const LaneInfo<VEC> &L, int32_t minfin)
+{
+    if (!F.post) return;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        if (!((L.fin_ok | L.fin_fail) >> k & 1)) continue;
+        F.postok[(int64_t)nxt * F.P.lanes + L.l0 + k] = stores_post(L.iter[k], F.P.maxiter, minfin) ? 1 : 0;
+        if ((L.fin_ok >> k & 1) && L.iter[k] > 0) {   // (0 iterations = input already consistent: copy path, no signal)
+#if defined(__CUDA_ARCH__)
+            atomicMin(&F.P.ctrl[CTRL_MINFIN_NEXT], L.iter[k]);
+#else
+            if (L.iter[k] < F.P.ctrl[CTRL_MINFIN_NEXT]) F.P.ctrl[CTRL_MINFIN_NEXT] = L.iter[k];
+#endif
+        }
+    }
 }
 
 template <typename T>

@@ -36,6 +36,8 @@ struct qr_decoder {
     int fused_tile = 32;     // lanes per L2 tile of the fused schedule (32, 64 or 128)
     int fused_pipe = 0;      // staging experiments (only with -DQR_FUSED_EXPERIMENTS): 1/2 cp.async stages, 3 TMA bulk rows
     int fused_prefetch = 0;  // 1: sequential L2 prefetch of the next tile (measured slower on B200)
+    int fused_store_post = 1;   // store posteriors of lanes that may finish (cheap shipping), 0: always rebuild them
+    int32_t *postok = nullptr;  // [2][lanes]
     int fused_static = 0;    // per mille of the claims dealt statically
     int fused_rpc = 4;       // checks per thread and claim of the register-staged fused phase
     int fused_hints = 1;     // L2 policy of the fused schedule: 0 none, 1 stores evict-first, 2 + loads evict-last

@@ -117,7 +117,7 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
 template <typename T, int VEC>
 static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *llr, int llr_dtype,
                               const uint8_t *synd, int64_t frames, int maxiter, uint8_t *success, int32_t *iters,
-                              void *post, int post_dtype, int64_t *steps_out)
+                              void *post, int post_dtype, int64_t *steps_out, int store_post, int64_t *shipped_out)
 {
     if (g.slot_nbr.empty() || g.max_cdeg > kFusedMaxCheckDegree || lanes % tl) return -2;
     std::vector<T> c2v0((size_t)g.E * lanes, (T)1e30), c2v1((size_t)g.E * lanes, (T)-3e30), llrw((size_t)g.N * lanes, (T)3e29);
@@ -141,6 +141,9 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     F.nbr = reinterpret_cast<const Nbr4 *>(g.slot_nbr.data());
     F.c2v[0] = c2v0.data(); F.c2v[1] = c2v1.data();
     F.tl = tl; F.tiles = lanes / tl; F.hints = 0; F.prefetch = 0; F.rows_per_claim = 2; F.static_share = 0;
+    std::vector<T> postw((size_t)g.N * lanes, (T)-7e29);
+    std::vector<int32_t> postok(2 * lanes, 0);
+    F.post = store_post ? postw.data() : nullptr; F.postok = postok.data();
     for (int l = 0; l < lanes; ++l) {
         LaneState s;
         s.frame = l < frames ? l : -1; s.iter = 0; s.fresh = s.frame >= 0; s.retire = -1;
@@ -149,11 +152,15 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     ctrl[CTRL_NEXT_FRAME] = (int32_t)std::min<int64_t>(lanes, frames);
     ctrl[CTRL_REMAINING] = (int32_t)frames;
     ctrl[CTRL_FIN_STEP] = -1;
+    ctrl[CTRL_MINFIN] = ctrl[CTRL_MINFIN_NEXT] = 0x7fffffff;
+    int64_t shipped_from_post = 0;
     auto refill = [&](int buf, int cur) {
         for (int lane = 0; lane < lanes; ++lane) {
             const LaneState s = P.st[buf][lane];
             if (!lane_needs_refill(s)) continue;
-            for (int32_t n = 0; n < g.N; ++n) fused_refill_var_elem<T>(F, cur, s, lane, n);
+            const bool pv = F.post && s.retire >= 0 && F.postok[(size_t)buf * lanes + lane] != 0;
+            if (pv && P.iters[s.retire] != 0) ++shipped_from_post;
+            for (int32_t n = 0; n < g.N; ++n) fused_refill_var_elem<T>(F, cur, s, lane, n, pv);
             for (int32_t ci = 0; ci < g.C; ++ci) fused_refill_chk_elem<T>(F, s, lane, ci);
         }
     };
@@ -162,10 +169,12 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     for (; ctrl[CTRL_REMAINING] > 0; ++step) {
         if (step > (frames + lanes) * (int64_t)(maxiter + 3)) return -1;
         const int cur = step & 1;
+        const int32_t minfin = ctrl[CTRL_MINFIN];
         for (int tile = 0; tile < F.tiles; ++tile) {
             const TileView<T> V = tile_view(F, cur, tile);
             for (int tx = 0; tx < tl / VEC; ++tx) {
-                const LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, (tile * tl) / VEC + tx);
+                LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, (tile * tl) / VEC + tx);
+                mark_post_lanes<T, VEC>(F, L, minfin);
                 if (!L.active) continue;
                 uint32_t bad = 0;
                 for (const CheckBin &bin : g.bins)
@@ -178,10 +187,13 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
         for (int jv = 0; jv < lanes / VEC; ++jv) {
             LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
             decide_lanes<T, VEC>(P, cur, L);
+            fused_note_finishers<T, VEC>(F, cur ^ 1, L, minfin);
             bookkeep_lanes<T, VEC>(P, cur, (int32_t)step, L);
         }
+        ctrl[CTRL_MINFIN] = ctrl[CTRL_MINFIN_NEXT];
         if (ctrl[CTRL_FIN_STEP] == step) refill(cur ^ 1, cur);
     }
+    if (shipped_out) *shipped_out = shipped_from_post;
     if (steps_out) *steps_out = step;
     return 0;
 }
@@ -222,16 +234,17 @@ int emu_decode(const int64_t *vid, const int64_t *cid, int64_t E, int precision,
 
 int emu_decode_fused(const int64_t *vid, const int64_t *cid, int64_t E, int precision, int lanes, int tile_lanes,
                      const void *llr, int llr_dtype, const uint8_t *synd, int64_t frames, int maxiter,
-                     uint8_t *success, int32_t *iters, void *post, int post_dtype, int64_t *steps)
+                     uint8_t *success, int32_t *iters, void *post, int post_dtype, int64_t *steps, int store_post,
+                     int64_t *shipped_from_post)
 {
     qr_graph g;
     int rc = build_host_tables(g, vid, cid, E);
     if (rc) return rc;
     if (precision == QR_F64)
         return emu_decode_fused_t<double, 2>(g, lanes, tile_lanes, llr, llr_dtype, synd, frames, maxiter, success,
-                                             iters, post, post_dtype, steps);
+                                             iters, post, post_dtype, steps, store_post, shipped_from_post);
     return emu_decode_fused_t<float, 4>(g, lanes, tile_lanes, llr, llr_dtype, synd, frames, maxiter, success, iters,
-                                        post, post_dtype, steps);
+                                        post, post_dtype, steps, store_post, shipped_from_post);
 }
 
 // mapper arithmetic: mode bit 0 = fast inverse, bit 1 = corrected exponent

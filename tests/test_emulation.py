@@ -44,7 +44,8 @@ def emu_decode(vid, cid, llr, synd, maxiter, precision=F64, lanes=32, generic=0,
     return ok, it, post, steps.value
 
 
-def emu_decode_fused(vid, cid, llr, synd, maxiter, precision=F64, lanes=32, tile_lanes=32, post_dtype=F64):
+def emu_decode_fused(vid, cid, llr, synd, maxiter, precision=F64, lanes=32, tile_lanes=32, post_dtype=F64,
+                     store_post=1, want_shipped=False):
     L = load()
     vid = np.ascontiguousarray(vid, dtype=np.int64); cid = np.ascontiguousarray(cid, dtype=np.int64)
     llr = np.ascontiguousarray(llr); synd = np.ascontiguousarray(synd, dtype=np.uint8)
@@ -52,12 +53,15 @@ def emu_decode_fused(vid, cid, llr, synd, maxiter, precision=F64, lanes=32, tile
     ok = np.full(frames, 255, dtype=np.uint8); it = np.full(frames, -1, dtype=np.int32)
     post = np.zeros((frames, N), dtype=np.float64 if post_dtype == F64 else np.float32)
     steps = C.c_int64(0)
+    shipped = C.c_int64(0)
     rc = L.emu_decode_fused(ptr(vid), ptr(cid), C.c_int64(vid.size), precision, lanes, tile_lanes, ptr(llr),
                             F64 if llr.dtype == np.float64 else F32, ptr(synd), C.c_int64(frames), maxiter, ptr(ok),
-                            ptr(it), ptr(post), post_dtype, C.byref(steps))
+                            ptr(it), ptr(post), post_dtype, C.byref(steps), store_post, C.byref(shipped))
     if rc == -2:
         return None   # graph not eligible for the fused schedule (variable degree != 3 or a check degree > 8)
     assert rc == 0, L.emu_last_error()
+    if want_shipped:
+        return ok, it, post, steps.value, shipped.value
     return ok, it, post, steps.value
 
 
@@ -141,8 +145,9 @@ def test_emulated_fused_schedule_chain_bit_exact():
                 llr = g[f"s{si}_{lk}"]; synd = g[f"s{si}_{sk}"]
                 if not np.all(np.isfinite(llr)):
                     continue
-                for lanes, tl in ((32, 32), (64, 32), (64, 64)):
-                    r = emu_decode_fused(g["vid"], g["cid"], llr, synd, int(g["maxiter"]), lanes=lanes, tile_lanes=tl)
+                for lanes, tl, sp in ((32, 32, 1), (64, 32, 0), (64, 64, 1)):
+                    r = emu_decode_fused(g["vid"], g["cid"], llr, synd, int(g["maxiter"]), lanes=lanes, tile_lanes=tl,
+                                         store_post=sp)
                     if r is None:
                         continue
                     ok, it, post, _ = r
@@ -168,12 +173,22 @@ def test_emulated_fused_schedule_edge_cases_match_two_phase():
     llr[7, :4] = -0.0
     for maxiter in (0, 1, 12):
         want = [dec.decode(llr[f], synd[f], maxiter) for f in range(frames)]
-        for lanes, tl in ((32, 32), (64, 32), (128, 64)):
-            ok, it, post, _ = emu_decode_fused(vid, cid, llr, synd, maxiter, lanes=lanes, tile_lanes=tl)
+        for lanes, tl, sp in ((32, 32, 1), (64, 32, 1), (128, 64, 1), (32, 32, 0)):
+            ok, it, post, _, shipped = emu_decode_fused(vid, cid, llr, synd, maxiter, lanes=lanes, tile_lanes=tl,
+                                                        store_post=sp, want_shipped=True)
             assert [int(o) for o in ok] == [w[0] for w in want]
             assert [int(i) for i in it] == [w[1] for w in want]
             for f in range(frames):
                 assert same_bits(post[f], want[f][2]), (maxiter, lanes, f)
+            # posteriors stored by the phase serve the frames that finish at the iteration limit or no earlier
+            # than one below the earliest success seen so far; the others are rebuilt -- same bits either way
+            iterated = sum(1 for w in want if w[1] > 0)
+            if sp == 0:
+                assert shipped == 0
+            elif maxiter > 0:
+                assert 0 < shipped <= iterated
+                if maxiter == 12 and lanes == 32:
+                    assert shipped >= iterated // 2 and shipped < iterated    # both paths exercised
     # fp32: same decisions as the two-phase fp32 schedule, frame by frame
     ok2, it2, post2, _ = emu_decode(vid, cid, llr.astype(np.float32), synd, 12, precision=F32, post_dtype=F32)
     ok3, it3, post3, _ = emu_decode_fused(vid, cid, llr.astype(np.float32), synd, 12, precision=F32, lanes=64,

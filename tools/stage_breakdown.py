@@ -31,7 +31,8 @@ for rep in range(3):
     _, nh, word = nm.front_end_batch(y, want_index=False); t.append(ev())
     synd = mat.eval_syndrome_batch(word); t.append(ev())
     llr = nm.demap_lappr_array_batch(nh, x, mode="fast", out_dtype=torch.float32); t.append(ev())
-    ok, it, post = dec.decode_batch(llr, synd, 50, precision="fp32"); t.append(ev())
+    ok, it, post = dec.decode_batch(llr, synd, 50, precision="fp32", schedule=int(os.environ.get("SCHEDULE", "2")),
+                                    lanes=int(os.environ.get("LANES", "1024"))); t.append(ev())
     err = utils.count_errors_batch(post, word, k=32400); t.append(ev())
     torch.cuda.synchronize()
     names = ["front_end", "syndrome", "demap", "decode", "count_errors"]
