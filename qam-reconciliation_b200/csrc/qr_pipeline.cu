@@ -9,6 +9,8 @@
 // caller's stream.
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include <algorithm>
 #include <cstring>
 
@@ -164,7 +166,18 @@ extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, in
     int64_t chunk = std::max<int64_t>(2 * (int64_t)d->lanes, (frames + 7) / 8);
     chunk = std::min<int64_t>(chunk, std::max<int64_t>((int64_t)d->lanes, (frames + 3) / 4));
     chunk = std::min(chunk, frames);
-    const int64_t n_chunks = (frames + chunk - 1) / chunk;
+    // The first chunk's upload and the last chunk's download cannot hide behind kernels: make those two chunks
+    // small (a quarter of a chunk, at least 32 frames) whenever the batch is cut at all.
+    std::vector<int64_t> cuts;    // chunk boundaries: cuts[c] .. cuts[c + 1]
+    cuts.push_back(0);
+    if (chunk < frames) {
+        const int64_t small = std::max<int64_t>(32, chunk / 4 / 32 * 32);
+        cuts.push_back(std::min(small, frames));
+        while (frames - cuts.back() > chunk + small) cuts.push_back(cuts.back() + chunk);
+        if (frames - cuts.back() > small) cuts.push_back(frames - small);
+    }
+    if (cuts.back() < frames) cuts.push_back(frames);
+    const int64_t n_chunks = (int64_t)cuts.size() - 1;
     const int n_sets = n_chunks > 1 ? 2 : 1;
 
     if (!d->pipe_streams_ready) {
@@ -202,7 +215,7 @@ extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, in
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int s = (int)(c % n_sets);
         const Buffers &b = sets[s];
-        const int64_t f0 = c * chunk, nf = std::min(chunk, frames - f0);
+        const int64_t f0 = cuts[c], nf = cuts[c + 1] - cuts[c];
         // stage 1: inputs of chunk c (the set is free once the kernels of chunk c-2 are done)
         if (c >= n_sets) QR_CUDA_CHECK(cudaStreamWaitEvent(d->s_in, d->ev_compute[s], 0));
         QR_CUDA_CHECK(cudaMemcpyAsync(b.y, h_y + f0 * S, nf * S * sizeof(double), cudaMemcpyHostToDevice, d->s_in));
