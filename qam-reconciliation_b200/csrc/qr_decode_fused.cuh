@@ -117,7 +117,7 @@ QR_HD TileView<T> tile_view(const FusedParams<T> &F, int cur, int32_t tile)
 {
     TileView<T> V;
     V.tl = F.tl;
-    V.item_prefetch = (F.prefetch >> 1) & 1;
+    V.item_prefetch = (F.prefetch >> 1) & 3;   // bit 0: next item's rows into L2, bit 1: next item's records into L1
     V.c_old = F.c2v[cur] + (int64_t)tile * F.P.E * F.tl;
     V.c_new = F.c2v[cur ^ 1] + (int64_t)tile * F.P.E * F.tl;
     V.llr = F.P.llr + (int64_t)tile * F.P.N * F.tl;
@@ -240,7 +240,7 @@ QR_HD uint32_t run_fused_bin(const TileView<T> &V, const Nbr4 *nbr, const LaneIn
         // held, and the demand loads of the next item find their compulsory DRAM misses already in L2.
         for (int32_t k = first; k < bin.count; k += stride) {
 #if defined(__CUDA_ARCH__)
-            if (V.item_prefetch && k + stride < bin.count) {
+            if ((V.item_prefetch & 1) && k + stride < bin.count) {
                 const int32_t *raw = reinterpret_cast<const int32_t *>(nbr + bin.slot_begin + (k + stride) * D);
                 const int32_t bx = V.tl / VEC, tx = lt / VEC;
                 for (int32_t r = tx; r < 4 * D; r += bx) {
@@ -248,6 +248,14 @@ QR_HD uint32_t run_fused_bin(const TileView<T> &V, const Nbr4 *nbr, const LaneIn
                     const T *row = (r & 3) == 0 ? V.llr + (int64_t)(id & 0x0fffffff) * V.tl : V.c_old + (int64_t)id * V.tl;
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(row));
                 }
+            }
+#endif
+#if defined(__CUDA_ARCH__)
+            if ((V.item_prefetch & 2) && k + stride < bin.count) {
+                // the neighbour records of the NEXT item into L1: its first dependent load then costs an L1 hit
+                const Nbr4 *nx = nbr + bin.slot_begin + (k + stride) * D;
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(nx));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(nx + D - 1));
             }
 #endif
             Nbr4 cur[D];
