@@ -79,6 +79,7 @@ struct qr_mapper {
     double *inv_tab = nullptr;   // F_Y on a uniform grid, see MapperView
     double *inv_pdf = nullptr;   // its density on the same grid (second half of the same allocation)
     int32_t inv_n = 0;
+    int32_t uniform = 1;           // equally spaced constellation
     int32_t *inv_jump = nullptr;   // InvTable::jump
     int32_t inv_jn = 0;
     double inv_y0 = 0, inv_h = 0;

@@ -20,6 +20,7 @@ static MapperView view_of(const qr_mapper *m)
     v.sign_config = m->d_sign; v.sign_g = m->d_sign_g; v.FY_thr = m->FY_thr; v.delta = m->delta; v.bare = m->bare;
     v.inv_tab = m->inv_tab; v.inv_pdf = m->inv_pdf; v.inv_n = m->inv_n; v.inv_y0 = m->inv_y0; v.inv_h = m->inv_h;
     v.inv_jump = m->inv_jump; v.inv_jn = m->inv_jn;
+    v.uniform = m->uniform;
     return v;
 }
 
@@ -120,7 +121,8 @@ __global__ void __launch_bounds__(128) k_demap(MapperView m, const double *__res
 {
     __shared__ SharedTables s;
     stage_tables(m, s);
-    const TablesRef t = tables_ref(s);
+    TablesRef t = tables_ref(s);
+    if (!m.uniform) t.ghi = t.glo = nullptr;
     for (int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sidx < n;
          sidx += (int64_t)gridDim.x * blockDim.x) {
         double out[kMaxBps];
@@ -201,6 +203,10 @@ int qr_mapper_create(int bits_per_symbol, const double *h_constellation, const d
     m->noise_var = noise_var;
     m->sigma = sqrt(noise_var);
     m->s2 = sqrt(2.0) * m->sigma;
+    m->uniform = 1;
+    for (int i = 2; i < M; ++i)
+        if (fabs((h_constellation[i] - h_constellation[i - 1]) - (h_constellation[1] - h_constellation[0])) >
+            1e-12 * fabs(h_constellation[1] - h_constellation[0])) m->uniform = 0;
     qr::DeviceGuard guard(device);
     auto body = [&]() -> int {
         const size_t nd = (size_t)M + (M + 1) + M + (M + 1) + M + 3 * (size_t)M * M + (size_t)M * bits_per_symbol;

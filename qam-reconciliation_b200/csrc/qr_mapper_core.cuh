@@ -32,6 +32,7 @@ struct MapperView {
     double inv_y0, inv_h;
     const int32_t *inv_jump;      // see InvTable::jump
     int32_t inv_jn;
+    int32_t uniform;              // constellation points equally spaced (always true for PAMAlphabet): enables E^m G[m]
 };
 
 struct InvTable {
@@ -458,6 +459,7 @@ QR_HD void demap_from_yhat(const double *a, const double *p, const double *delta
 struct TablesRef {
     const double *a, *p, *thr, *FYt, *delta;
     const uint8_t *sign;
+    const double *ghi = nullptr, *glo = nullptr, *pz = nullptr;   // see SharedTables (fast demapper only)
 };
 
 // demap_lappr (noisemapper.pyx:450-540) for ONE symbol: Bob's metric n_hat, Alice's symbol j -> bps
@@ -478,6 +480,34 @@ QR_HD void demap_symbol(const MapperView &m, const TablesRef &s, double nv, int3
                                             InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h, m.inv_jump, m.inv_jn})
                                : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
         double sum = 0;
+        // Fast mode, uniform constellation: with d = y_hat - a_j and a_k - a_j = m step the exponent is
+        // (2 d - m step)(m step) c = m (2 d step c) - (m step)^2 c, so exp of it = E^m G[m] with ONE exp per side
+        // (E = exp(2 d step c); c = 1 / 2 sigma^2 for k > j and -- the reference's quirk -- 1 for k < j) and
+        // G tabulated.  Falls back to the direct form if a power could overflow.
+        const int M = m.order;
+        const double step = M > 1 ? s.a[1] - s.a[0] : 0.0, dd = yh - s.a[j];
+        const double u_hi = 2 * dd * step * inv_two_s2, u_lo = -2 * dd * step * (corrected ? inv_two_s2 : 1.0);
+        if (fast && s.ghi && fabs(u_hi) * (M - 1) < 600.0 && fabs(u_lo) * (M - 1) < 600.0) {
+            // the same instruction stream whatever j (threads of a warp hold different j): both sides always run
+            // all M - 1 powers, against probabilities zero-padded outside the alphabet
+            const double *glo = corrected ? s.ghi : s.glo;
+            const double *pj = s.pz + (M - 1) + j;
+            const double Eh = exp(u_hi), El = exp(u_lo);
+            double ph = 1.0, pl = 1.0;
+            sum = s.p[j];
+            for (int mm = 1; mm < M; ++mm) {
+                ph *= Eh; pl *= El;
+                sum += pj[mm] * (ph * s.ghi[mm]) + pj[-mm] * (pl * glo[mm]);
+            }
+            const double w = s.delta[i] / sum;
+            int q = i;
+            for (int k = 0; k < m.bps; ++k) {
+                if ((q * (q + 1)) & 3) D[k] += w;
+                else N[k] += w;
+                q >>= 1;
+            }
+            continue;
+        }
         for (int k = 0; k < j; ++k) {
             double ex = mul_rn(add_rn(add_rn(mul_rn(2, yh), -s.a[k]), -s.a[j]), add_rn(s.a[k], -s.a[j]));
             if (corrected) ex = fast ? ex * inv_two_s2 : ex / two_s2;

@@ -73,9 +73,10 @@ def test_paired_frames_against_oracle(setup, mode):
     assert 0 < want[:, 1].sum() < frames or mode != 0       # the soft-RR point sits in the waterfall
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp64"])
-def test_monte_carlo_statistics_within_confidence_intervals(setup, precision, monkeypatch):
-    """BER / FER / average iterations of simulate_softening_snr_dB against the oracle's own Monte Carlo."""
+@pytest.mark.parametrize("precision,schedule", [("fp32", "0"), ("fp64", "0"), ("fp32", "3")])
+def test_monte_carlo_statistics_within_confidence_intervals(setup, precision, schedule, monkeypatch):
+    """BER / FER / average iterations of simulate_softening_snr_dB against the oracle's own Monte Carlo
+    (schedule 3 = the fused flooding iteration where the graph allows it)."""
     s = setup
     from sims.reconciliation import simulate_softening_snr_dB
     snr = 4.3
@@ -90,6 +91,7 @@ def test_monte_carlo_statistics_within_confidence_intervals(setup, precision, mo
     it_ref = ref[ref[:, 1] == 1, 2].mean()
     monkeypatch.setenv("QAMRECON_PRECISION", precision)
     monkeypatch.setenv("QAMRECON_DEMAP", "fast" if precision == "fp32" else "exact")
+    monkeypatch.setenv("QAMRECON_SCHEDULE", schedule)
     np.random.seed(5)
     n_gpu = 4000
     snr_out, ber, fer, avg_it = simulate_softening_snr_dB(snr, s["dec"], s["mat"], pa, s["cfg"], 50, n_gpu, 10 ** 9)
