@@ -1,3 +1,5 @@
+#!/usr/bin/env python3
+"""Demapper cost split on the GPU: whole fast demapper vs. one inverse per element (development tool)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "qam-reconciliation_b200"))
