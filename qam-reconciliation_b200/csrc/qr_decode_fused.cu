@@ -632,7 +632,7 @@ __device__ __forceinline__ void fused_refill_phase(const FusedParams<T> &F, int 
 }
 
 template <typename T, int VEC, int DSEL, int PIPE>   // PIPE: 0 register-staged, 1 / 2 = cp.async stages per thread
-__global__ void __launch_bounds__(kFBlock, (PIPE == 1 || (PIPE == 3 && sizeof(T) == 4) || (PIPE == 0 && sizeof(T) == 4 && DSEL > 0)) ? 2 : 1) k_fused(FusedParams<T> F)
+__global__ void __launch_bounds__(kFBlock, (PIPE == 1 || (PIPE == 3 && sizeof(T) == 4) || (PIPE == 0 && DSEL > 0)) ? 2 : 1) k_fused(FusedParams<T> F)
 {
     extern __shared__ uint4 dyn_stage[];   // PIPE stages x 4 DSEL rows x kFBlock threads x 16 B
     __shared__ uint64_t s_bars[kFBlock / 2];   // PIPE == 3: one mbarrier per group of bx threads
