@@ -5,8 +5,9 @@
 // one L2-sized tile at a time) -> the LAST CTA to finish it advances the lane state machine for all lanes
 // -> grid barrier -> (only if a frame finished) refill phase -> grid barrier.
 //
-// Thread mapping of the fused phase: a CTA of 256 threads is bx = TL / VEC threads along the lanes of a
-// tile row (so bx threads move one contiguous TL * w byte row) times by = 256 / bx checks.
+// Thread mapping of the fused phase: bx = TL / VEC threads share a check (together they move one contiguous
+// TL * w byte row per access), a warp is 32 / bx checks wide, and WARPS claim work from one counter (see
+// fused_phase); fp32: 128 registers, two CTAs of 256 threads per SM.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
