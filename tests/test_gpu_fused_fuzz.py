@@ -1,0 +1,84 @@
+"""Randomised differential test of the fused flooding-iteration schedule against the two-phase schedule:
+random (3, k)-regular and variable-regular-3 codes, frame counts, lane counts, iteration limits, noise levels,
+inconsistent syndromes.  fp64: success flags, iteration counts and posteriors must be BIT-identical (the two
+schedules restate the same arithmetic); fp32: the same flags, iteration counts within 1, same hard decisions on
+converged frames.  Catches ordering bugs in the work claims, the bookkeeping and the two shipping paths."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+
+def frames_for(orc, vid, cid, frames, rng):
+    mat = orc.Matrix(vid, cid)
+    n = mat.vnum
+    word = rng.integers(0, 2, size=(frames, n)).astype(np.uint8)
+    sigma = rng.choice([0.55, 0.75, 0.9, 1.2], size=(frames, 1))
+    llr = 2 * ((1 - 2.0 * word) + sigma * rng.normal(size=word.shape)) / sigma ** 2
+    synd = np.array([mat.eval_syndrome(w) for w in word])
+    bad = rng.random(frames) < 0.2
+    synd[bad, :2] ^= 1                                   # frames that cannot converge
+    easy = rng.random(frames) < 0.1
+    llr[easy] = np.where(word[easy] == 1, -4.0, 4.0)     # frames that are consistent from the start (0 iterations)
+    synd[easy] = np.array([mat.eval_syndrome(w) for w in word[easy]]) if easy.any() else synd[easy]
+    return llr, synd
+
+
+def mixed_check_degrees(codes, n, rng):
+    """every variable of degree 3, check degrees drawn from 4..8 (the generic fused kernel, several degree bins)"""
+    sockets = 3 * n
+    degs = []
+    while sum(degs) < sockets:
+        degs.append(int(rng.integers(4, 9)))
+    over = sum(degs) - sockets
+    while over > 0:                                   # trim without leaving the 4..8 range
+        i = int(rng.integers(0, len(degs)))
+        if degs[i] > 4:
+            degs[i] -= 1; over -= 1
+    vsock = np.repeat(np.arange(n), 3); rng.shuffle(vsock)
+    csock = np.repeat(np.arange(len(degs)), degs)
+    vsock = codes._repair_duplicates(vsock, csock, rng)
+    return codes._finish(vsock, csock)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fused_equals_two_phase(seed):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import qamreconciliation as qr
+    from qamreconciliation import codes
+    from oracle import port as orc
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([96, 240, 648, 1296]))
+    kind = seed % 3
+    if kind == 0:
+        vid, cid = codes.regular_ldpc(n, 3, 6, seed=seed)                 # check-regular: the specialised kernel
+    elif kind == 1:
+        vid, cid = codes.regular_ldpc(n, 3, 3, seed=seed)                 # (3,3): generic fused path, degree 3
+    else:
+        vid, cid = mixed_check_degrees(codes, n, rng)                      # variable degree 3, check degrees 4..8
+    frames = int(rng.integers(1, 220))
+    lanes = int(rng.choice([32, 64, 96, 128]))
+    maxiter = int(rng.choice([0, 1, 3, 10, 25]))
+    llr, synd = frames_for(orc, vid, cid, frames, rng)
+    dec = qr.Decoder(vid, cid)
+    a = dec.decode_batch(llr, synd, maxiter, precision="fp64", lanes=lanes, schedule=0)
+    b = dec.decode_batch(llr, synd, maxiter, precision="fp64", lanes=lanes, schedule=2)
+    assert torch.equal(a[0], b[0]), (seed, "success")
+    assert torch.equal(a[1], b[1]), (seed, "iterations")
+    assert torch.equal(a[2].view(torch.int64), b[2].view(torch.int64)), (seed, "posteriors")
+    l32 = torch.tensor(llr, dtype=torch.float32)
+    a32 = dec.decode_batch(l32, synd, maxiter, precision="fp32", lanes=lanes, schedule=0)
+    b32 = dec.decode_batch(l32, synd, maxiter, precision="fp32", lanes=lanes, schedule=2)
+    assert torch.equal(a32[0], b32[0]), (seed, "fp32 success")
+    assert int((a32[1] - b32[1]).abs().max()) <= 1
+    conv = a32[0].bool()
+    assert torch.equal(a32[2][conv] < 0, b32[2][conv] < 0)
+    # the oracle agrees with both on a few frames
+    odec = orc.Decoder(vid, cid)
+    for f in range(min(frames, 4)):
+        ok, it, post = odec.decode(llr[f], synd[f], maxiter)
+        assert (int(a[0][f]), int(a[1][f])) == (ok, it)
+        np.testing.assert_allclose(a[2][f].cpu().numpy(), post, rtol=1e-9, atol=1e-9)
