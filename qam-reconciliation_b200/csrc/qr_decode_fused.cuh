@@ -72,13 +72,20 @@ template <typename V>
 QR_HD V ld_pol(const V *p, uint64_t pol)
 {
 #if defined(__CUDA_ARCH__)
-    static_assert(sizeof(V) == 16, "fused schedule moves 16-byte lane vectors");
-    uint32_t r0, r1, r2, r3;
-    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "l"(p), "l"(pol));
-    uint32_t t[4] = {r0, r1, r2, r3};
+    static_assert(sizeof(V) == 16 || sizeof(V) == 8, "fused schedule moves 16- or 8-byte lane vectors");
     V v;
-    memcpy(&v, t, 16);
+    if constexpr (sizeof(V) == 16) {
+        uint32_t r0, r1, r2, r3;
+        asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "l"(p), "l"(pol));
+        uint32_t t[4] = {r0, r1, r2, r3};
+        memcpy(&v, t, 16);
+    } else {
+        uint32_t r0, r1;
+        asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(r0), "=r"(r1) : "l"(p), "l"(pol));
+        uint32_t t[2] = {r0, r1};
+        memcpy(&v, t, 8);
+    }
     return v;
 #else
     (void)pol;
@@ -89,11 +96,18 @@ template <typename V>
 QR_HD void st_pol(V *p, const V &val, uint64_t pol)
 {
 #if defined(__CUDA_ARCH__)
-    static_assert(sizeof(V) == 16, "fused schedule moves 16-byte lane vectors");
-    uint32_t t[4];
-    memcpy(t, &val, 16);
-    asm volatile("st.global.cg.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
-                 :: "l"(p), "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "l"(pol) : "memory");
+    static_assert(sizeof(V) == 16 || sizeof(V) == 8, "fused schedule moves 16- or 8-byte lane vectors");
+    if constexpr (sizeof(V) == 16) {
+        uint32_t t[4];
+        memcpy(t, &val, 16);
+        asm volatile("st.global.cg.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
+                     :: "l"(p), "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "l"(pol) : "memory");
+    } else {
+        uint32_t t[2];
+        memcpy(t, &val, 8);
+        asm volatile("st.global.cg.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" :: "l"(p), "r"(t[0]), "r"(t[1]), "l"(pol)
+                     : "memory");
+    }
 #else
     (void)pol;
     *p = val;
