@@ -48,7 +48,7 @@ extern "C" {
 #define QR_SCHED_FUSED 2      /* check update + variable sums + syndrome test in ONE pass per iteration, two
                                  message buffers, L2-sized lane tiles; needs variable degree 3 everywhere and
                                  check degrees <= 8 (QR_ERR_INVALID otherwise); same results */
-#define QR_SCHED_AUTO 3       /* QR_SCHED_FUSED where the graph allows it, else QR_SCHED_PERSISTENT */
+#define QR_SCHED_AUTO 3       /* QR_SCHED_FUSED where the graph allows it, else QR_SCHED_PERSISTENT (the default) */
 
 typedef struct qr_graph qr_graph;
 typedef struct qr_decoder qr_decoder;

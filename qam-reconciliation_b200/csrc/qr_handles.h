@@ -26,7 +26,7 @@ MapperView mapper_view(const qr_mapper *m);
 struct qr_decoder {
     const qr_graph *g = nullptr;
     int precision = QR_F32;
-    int schedule = QR_SCHED_PERSISTENT;
+    int schedule = QR_SCHED_AUTO;   // fused flooding iteration where the graph allows it, else the two-phase kernel
     int32_t lanes = 0;
     int device = 0;
     int regular_degree = 0;  // > 0: check-regular graph with a specialised kernel

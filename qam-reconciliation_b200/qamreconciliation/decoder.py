@@ -60,7 +60,7 @@ class Decoder:
         if lanes is None:
             lanes = int(os.environ.get("QAMRECON_LANES", "0"))
         if schedule is None:
-            schedule = int(os.environ.get("QAMRECON_SCHEDULE", str(_abi.QR_SCHED_PERSISTENT)))
+            schedule = int(os.environ.get("QAMRECON_SCHEDULE", str(_abi.QR_SCHED_AUTO)))
         key = (precision, lanes)
         if key not in self._dec:
             h = C.c_void_p()
