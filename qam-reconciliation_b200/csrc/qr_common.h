@@ -56,6 +56,10 @@ struct qr_graph {
     std::vector<int32_t> var_ptr;    // [N+1]
     std::vector<int32_t> var_slot;   // [E]   per variable, CSR slots in ascending edge id
     std::vector<qr::CheckBin> bins;
+    // variable ids sorted by degree (stable): neighbouring work items of the variable phase have the same degree,
+    // so a warp runs one unrolled code path; empty when every variable has the same degree
+    std::vector<int32_t> var_work;   // [N]
+    int32_t *d_var_work = nullptr;
     // fused schedule (var_deg == 3 only): per CSR slot {variable | own position << 28, the variable's three
     // CSR slots in ascending edge id}; empty otherwise
     std::vector<int32_t> slot_nbr;   // [4 * E]

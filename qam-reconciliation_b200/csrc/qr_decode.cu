@@ -90,7 +90,7 @@ __device__ __forceinline__ void check_phase(const DecodeParams<T> &P, int cur, c
     }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, bool UNROLLED>
 __device__ __forceinline__ void var_phase(const DecodeParams<T> &P, int cur, int32_t step, const Tiling tl)
 {
     const int32_t tx = threadIdx.x % tl.bx, ty = threadIdx.x / tl.bx;
@@ -102,7 +102,7 @@ __device__ __forceinline__ void var_phase(const DecodeParams<T> &P, int cur, int
         const int32_t jv = xt * tl.bx + tx;
         LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
         decide_lanes<T, VEC>(P, cur, L);
-        run_var_range<T, VEC>(P, L, byid * tl.by + ty, gy * tl.by, (int32_t)P.N);
+        run_var_range<T, VEC, UNROLLED>(P, L, byid * tl.by + ty, gy * tl.by, (int32_t)P.N);
         if (byid == 0 && ty == 0) bookkeep_lanes<T, VEC>(P, cur, step, L);
     }
 }
@@ -170,7 +170,7 @@ __device__ __forceinline__ void check_phase_dyn(const DecodeParams<T> &P, int cu
     }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, bool UNROLLED>
 __device__ __forceinline__ void var_phase_dyn(const DecodeParams<T> &P, int cur, int32_t step, const Tiling tl,
                                               int32_t *s_base)
 {
@@ -190,7 +190,7 @@ __device__ __forceinline__ void var_phase_dyn(const DecodeParams<T> &P, int cur,
             __syncthreads();
             const int32_t n0 = *s_base;
             if (n0 >= N) break;
-            run_var_range<T, VEC>(P, L, n0 + ty, tl.by, min(n0 + claim, N));
+            run_var_range<T, VEC, UNROLLED>(P, L, n0 + ty, tl.by, min(n0 + claim, N));
         }
         if (byid == 0 && ty == 0) bookkeep_lanes<T, VEC>(P, cur, step, L);
     }
@@ -295,7 +295,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kBlock, min_ctas<T, VEC>()) k_var(DecodeParams<T> P, int step, Tiling tl)
 {
     if (*(volatile int32_t *)&P.ctrl[CTRL_SNAPSHOT] == 0) return;
-    var_phase<T, VEC>(P, step & 1, step, tl);
+    var_phase<T, VEC, true>(P, step & 1, step, tl);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[1], 1ULL);
 }
 
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kBlock, min_ctas<T, VEC>()) k_persistent(Decod
     for (int step = 0;; ++step) {
         check_phase_dyn<T, VEC, DSEL>(P, step & 1, tl, s_flags, &s_base);
         grid.sync();
-        var_phase_dyn<T, VEC>(P, step & 1, step, tl, &s_base);
+        var_phase_dyn<T, VEC, DSEL == 0>(P, step & 1, step, tl, &s_base);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[1], 1ULL);
         grid.sync();
         if (*(volatile int32_t *)&P.ctrl[CTRL_FIN_STEP] == step) {   // a frame finished: ship it, refill its lane
@@ -386,6 +386,7 @@ static DecodeParams<T> make_params(const qr_decoder *d, const void *llr, int llr
     P.slot_var = g->d_slot_var;
     P.var_ptr = g->d_var_ptr;
     P.var_slot = g->d_var_slot;
+    P.var_work = g->d_var_work;
     P.N = g->N; P.C = g->C; P.E = g->E;
     P.var_deg = g->var_deg;
     // a batch smaller than the workspace uses a narrower layout, so no CTA is left with idle lanes only

@@ -63,6 +63,7 @@ struct DecodeParams {
     const CheckBin *bins;
     int32_t n_bins;
     const int32_t *chk_order, *slot_var, *var_ptr, *var_slot;
+    const int32_t *var_work;   // variable ids sorted by degree (null: every variable has degree var_deg)
     int64_t N, C, E;
     int32_t var_deg;  // > 0: every variable has this degree (var_slot row of n starts at n * var_deg)
     // workspace
@@ -526,7 +527,9 @@ QR_HD void run_var_fixed(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32
 }
 
 // All variables n = first, first+stride, ... < n_end for the thread's lanes (decisions already in L).
-template <typename T, int VEC>
+// UNROLLED: compile the per-degree unrolled variants for irregular variable degrees (kept out of the kernels
+// specialised for one check degree, whose register allocation they would disturb).
+template <typename T, int VEC, bool UNROLLED = true>
 QR_HD void run_var_range(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t first, int32_t stride,
                          int32_t n_end)
 {
@@ -537,8 +540,29 @@ QR_HD void run_var_range(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32
         run_var_fixed<T, VEC, 3, U>(P, L, first, stride, n_end, L.upd != (1u << VEC) - 1u);
         return;
     }
-    for (int32_t n = first; n < n_end; n += stride) var_item<T, VEC>(P, L, n);
+    // irregular variable degrees: positions first, first + stride, ... of the degree-sorted work list.  Within a
+    // warp the degree is (almost always) the same, so the unrolled variants issue all their row loads at once
+    // instead of one dependent load per edge.
+    if constexpr (!UNROLLED) {
+        for (int32_t pos = first; pos < n_end; pos += stride) var_item<T, VEC>(P, L, P.var_work ? P.var_work[pos] : pos);
+        return;
+    }
+    const bool masked = L.upd != (1u << VEC) - 1u;
+    for (int32_t pos = first; pos < n_end; pos += stride) {
+        const int32_t n = P.var_work ? P.var_work[pos] : pos;
+        const int32_t q0 = P.var_ptr[n], deg = P.var_ptr[n + 1] - q0;
+        switch (deg) {
+        case 2: { int32_t sl[2]; load_index_row<2>(P.var_slot, q0, sl); var_item_fixed<T, VEC, 2>(P, L, n, sl, masked); break; }
+        case 3: { int32_t sl[3]; load_index_row<3>(P.var_slot, q0, sl); var_item_fixed<T, VEC, 3>(P, L, n, sl, masked); break; }
+        case 4: { int32_t sl[4]; load_index_row<4>(P.var_slot, q0, sl); var_item_fixed<T, VEC, 4>(P, L, n, sl, masked); break; }
+        case 5: { int32_t sl[5]; load_index_row<5>(P.var_slot, q0, sl); var_item_fixed<T, VEC, 5>(P, L, n, sl, masked); break; }
+        case 6: { int32_t sl[6]; load_index_row<6>(P.var_slot, q0, sl); var_item_fixed<T, VEC, 6>(P, L, n, sl, masked); break; }
+        case 8: { int32_t sl[8]; load_index_row<8>(P.var_slot, q0, sl); var_item_fixed<T, VEC, 8>(P, L, n, sl, masked); break; }
+        default: var_item<T, VEC>(P, L, n); break;
+        }
+    }
 }
+
 
 // One thread per lane-vector advances the lane state machine, once per step.
 #if defined(__CUDA_ARCH__)

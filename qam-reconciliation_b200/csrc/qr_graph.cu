@@ -86,6 +86,7 @@ int qr_graph_create(const int64_t *h_vid, const int64_t *h_cid, int64_t n_edges,
             if ((r = qr::upload(&g->d_var_slot, g->var_slot))) return r;
             if ((r = qr::upload(&g->d_bins, g->bins))) return r;
             if (!g->slot_nbr.empty() && (r = qr::upload(&g->d_slot_nbr, g->slot_nbr))) return r;
+            if (!g->var_work.empty() && (r = qr::upload(&g->d_var_work, g->var_work))) return r;
             return QR_OK;
         };
         rc = body();
@@ -104,7 +105,7 @@ void qr_graph_destroy(qr_graph *g)
         cudaGetDevice(&prev);
         cudaSetDevice(g->device);
         cudaFree(g->d_chk_order); cudaFree(g->d_chk_ptr); cudaFree(g->d_slot_var);
-        cudaFree(g->d_var_ptr); cudaFree(g->d_var_slot); cudaFree(g->d_bins); cudaFree(g->d_slot_nbr);
+        cudaFree(g->d_var_ptr); cudaFree(g->d_var_slot); cudaFree(g->d_bins); cudaFree(g->d_slot_nbr); cudaFree(g->d_var_work);
         cudaSetDevice(prev);
     }
     delete g;

@@ -90,6 +90,13 @@ inline int build_host_tables(qr_graph &g, const int64_t *vid, const int64_t *cid
             g.var_slot[g.var_ptr[v] + fill[v]++] = edge_slot[e];
         }
     }
+    g.var_work.clear();
+    if (g.var_deg == 0) {
+        g.var_work.resize(N);
+        for (int64_t v = 0; v < N; ++v) g.var_work[v] = (int32_t)v;
+        std::stable_sort(g.var_work.begin(), g.var_work.end(),
+                         [&](int32_t a, int32_t b) { return vdeg[a] < vdeg[b]; });
+    }
     // neighbour table of the fused schedule: what a check needs to rebuild post[v] = llr[v] + sum c2v
     // (decoder.pyx:291-293) of each of its variables without a stored posterior
     g.slot_nbr.clear();

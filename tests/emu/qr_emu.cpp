@@ -51,6 +51,7 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
     P.bins = g.bins.data(); P.n_bins = (int32_t)g.bins.size();
     P.chk_order = g.chk_order.data(); P.slot_var = g.slot_var.data();
     P.var_ptr = g.var_ptr.data(); P.var_slot = g.var_slot.data();
+    P.var_work = g.var_work.empty() ? nullptr : g.var_work.data();
     P.N = g.N; P.C = g.C; P.E = g.E; P.lanes = lanes; P.var_deg = g.var_deg;
     P.c2v = c2v.data(); P.post = postw.data(); P.llr = llrw.data(); P.synd = syndw.data();
     P.st[0] = st.data(); P.st[1] = st.data() + lanes;
@@ -130,6 +131,7 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     P.bins = g.bins.data(); P.n_bins = (int32_t)g.bins.size();
     P.chk_order = g.chk_order.data(); P.slot_var = g.slot_var.data();
     P.var_ptr = g.var_ptr.data(); P.var_slot = g.var_slot.data();
+    P.var_work = g.var_work.empty() ? nullptr : g.var_work.data();
     P.N = g.N; P.C = g.C; P.E = g.E; P.lanes = lanes; P.var_deg = g.var_deg;
     P.c2v = nullptr; P.post = nullptr; P.llr = llrw.data(); P.synd = syndw.data();
     P.st[0] = st.data(); P.st[1] = st.data() + lanes;
