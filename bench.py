@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -98,6 +98,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
+    def wait_ready(self, timeout=5.0):
+        """Block until nvidia-smi has delivered its first sample: its start-up (NVML initialisation holds driver
+        locks for ~100 ms and delays kernel launches) must not fall into the timed region."""
+        t0 = time.time()
+        while self.proc and not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.01)
+        self.skip = len(self.samples)     # samples taken before the timed region are not "under load"
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -107,7 +115,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for s in self.samples:
+        skip = getattr(self, "skip", 0)
+        for s in (self.samples[skip:] or self.samples):
             f = [t.strip() for t in s.split(",")]
             if len(f) < 7:
                 continue
@@ -316,24 +325,31 @@ def ours(a):
         return rec.run_device(ys[i % n_sets], xs[i % n_sets], MAXITER, k_info=K)
 
     # ---- device-resident leg
-    for i in range(a.warmup):
-        out = step(i)
-    barrier()
+    # nvidia-smi is started BEFORE the warm-up: its start-up takes ~0.2 s, and a GPU left idle that long drops its
+    # clocks and spends the first ~25 ms of the timed region ramping them up again
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    for i in range(a.warmup):
+        out = step(i)
+    barrier()
+    sampler.skip = len(sampler.samples)       # samples taken before the timed region do not count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     dec_ev = []
+    counters = torch.zeros(5, dtype=torch.int64, device=dev)
+    b_frames = torch.tensor(B, dtype=torch.int64, device=dev)
     barrier()
     ev[0].record()
-    counters = torch.zeros(5, dtype=torch.int64, device=dev)
     frame_iters = 0
     for i in range(a.steps):
         out = step(a.warmup + i)
+        # (b_frames lives on the device: building it here would be a synchronous host-to-device copy every step,
+        # which stalls the launch queue behind the whole step)
         counters += torch.stack([out["bit_errors"].sum(dtype=torch.int64), (out["bit_errors"] > 0).sum(),
                                  out["success"].sum(dtype=torch.int64),
                                  (out["iters"].to(torch.int64) * out["success"].to(torch.int64)).sum(),
-                                 torch.tensor(B, device=dev)])
+                                 b_frames])
     ev[1].record()
     barrier()
     elapsed_ms = ev[0].elapsed_time(ev[1])
