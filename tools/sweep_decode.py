@@ -32,7 +32,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1024)
     ap.add_argument("--snr", type=float, default=3.0)
     ap.add_argument("--lanes", default="32,64,96,128,256,512,1024")
-    ap.add_argument("--schedules", default="0,1")
+    ap.add_argument("--schedules", default="0,2")
     ap.add_argument("--precisions", default="fp32")
     ap.add_argument("--maxiter", type=int, default=50)
     ap.add_argument("--stages", action="store_true")
@@ -64,7 +64,7 @@ def main():
         for sched in [int(s) for s in a.schedules.split(",")]:
           for combo in (a.fused.split(",") if sched == 2 else [""]):
             if combo:
-                parts = (combo.split(":") + ["0", "0", "2"])[:5] if combo.count(":") < 4 else combo.split(":")
+                parts = (combo.split(":") + ["0", "0", "4"])[:5] if combo.count(":") < 4 else combo.split(":")
                 os.environ["QAMRECON_FUSED_RPC"] = parts[4]
                 os.environ["QAMRECON_FUSED_STATIC"] = parts[5] if len(parts) > 5 else "0"
                 os.environ["QAMRECON_FUSED_PREFETCH"] = parts[3]
