@@ -67,7 +67,14 @@ int qr_device_count(int *count);
  * device < 0 builds the host tables only (no CUDA call), for tests. */
 int qr_graph_create(const int64_t *h_vid, const int64_t *h_cid, int64_t n_edges, int device,
                     qr_graph **out);
+/* Matrix.__cinit__ (matrix.pyx:21-38) accepts ANY edge list -- checks of degree 0 or 1, unused check ids, degrees
+ * above 64 -- and Matrix.eval_syndrome works on it; so does this variant (ids must still be >= 0).  A graph that
+ * does not meet the decoder's requirements is refused by qr_decoder_create and the single-node entry points. */
+int qr_graph_create_any(const int64_t *h_vid, const int64_t *h_cid, int64_t n_edges, int device,
+                        qr_graph **out);
 void qr_graph_destroy(qr_graph *g);
+/* *eligible = 1 when QR_SCHED_FUSED can run this graph (what QR_SCHED_AUTO goes by) */
+int qr_graph_fused_eligible(const qr_graph *g, int *eligible);
 /* Decoder.cnum/vnum/ednum (decoder.pyx:157-172), Matrix.cnum/vnum/ednum (matrix.pxd:24-27) */
 int qr_graph_info(const qr_graph *g, int64_t *n_vars, int64_t *n_checks, int64_t *n_edges,
                   int32_t *max_check_degree, int32_t *max_var_degree);
@@ -133,6 +140,11 @@ int qr_mapper_create(int bits_per_symbol, const double *h_constellation, const d
                      const double *h_probabilities, double noise_var, const uint8_t *h_sign_config,
                      int device, qr_mapper **out);
 void qr_mapper_destroy(qr_mapper *m);
+/* Symbol / region indices handed to the entry points below must lie in [0, order); the reference's bounds-checked
+ * Cython raises IndexError otherwise.  Kernels cannot raise: they count out-of-range indices (and compute on index
+ * 0 instead of reading out of bounds).  This call synchronises `stream`, returns the count since the last call
+ * and resets it; the Python classes raise IndexError when it is non-zero. */
+int qr_mapper_index_errors(qr_mapper *m, int64_t *count, void *stream);
 /* host copies: F_Y_thresholds[order+1], delta_F_Y[order], fwrd[order*order], back[order*order],
  * bare_llr_table[order*bps], inf_erf_table[order*order] (noisemapper.pxd:19-35); NULL to skip */
 int qr_mapper_tables(const qr_mapper *m, double *F_Y_thresholds, double *delta_F_Y, double *fwrd,

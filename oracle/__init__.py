@@ -5,7 +5,7 @@ algorithm, built with gcc by `oracle.build()`); `oracle.ref` runs the compiled,
 unmodified reference (oracle/_ref, built by oracle/build_ref.py) in a
 subprocess-safe way.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs may import this package; the product
-package never does (tests/test_no_oracle_in_product.py enforces it).
+package never does (tests/test_abi_and_host.py::test_product_never_touches_the_oracle enforces it).
 """
 import os
 import subprocess

@@ -11,7 +11,7 @@
  * --impl reference legs may load this library.  Nothing under
  * qam-reconciliation_b200/ links, imports or executes it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py runs this file
+ * Parity status: PINNED.  tests/test_oracle_golden.py runs this file
  * against the compiled reference in this container and against the committed
  * fixtures in tests/golden/ (generated from the compiled reference by
  * tests/golden/make_golden.py): integer outputs and the whole decoder are

@@ -49,6 +49,7 @@ struct qr_graph {
     int device = -1;
     int32_t max_cdeg = 0, max_vdeg = 0;
     int32_t var_deg = 0;  // > 0 when every variable node has this degree
+    bool decodable = true;  // every check has degree 2..kMaxCheckDegree (what the decoder needs; Matrix takes any graph)
     std::vector<int32_t> chk_order;  // [C]   internal check slot -> original check id
     std::vector<int32_t> chk_ptr;    // [C+1] internal check slot -> first CSR slot
     std::vector<int32_t> slot_edge;  // [E]   CSR slot -> original edge id

@@ -494,6 +494,8 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
     *out = nullptr;
     if (!g) return qr::fail(QR_ERR_INVALID, "null graph");
     if (g->device < 0) return qr::fail(QR_ERR_INVALID, "graph was built without a device");
+    if (!g->decodable)
+        return qr::fail(QR_ERR_GRAPH, "the decoder needs every check node of degree 2..64 (graph built with qr_graph_create_any)");
     if (precision != QR_F32 && precision != QR_F64)
         return qr::fail(QR_ERR_INVALID, "precision must be QR_F32 or QR_F64");
     if (lanes < 0 || lanes > (1 << 20)) return qr::fail(QR_ERR_INVALID, "bad lane count");
@@ -693,6 +695,7 @@ __global__ void k_check_synd_node(NodeEdges ne, int64_t check, const uint8_t *wo
 static int node_edges(const qr_graph *g, int64_t check, NodeEdges &ne)
 {
     if (check < 0 || check >= g->C) return fail(QR_ERR_INVALID, "check node index out of range");
+    if (!g->decodable) return fail(QR_ERR_GRAPH, "the decoder needs every check node of degree 2..64");
     int32_t slot = -1;
     for (int64_t s = 0; s < g->C; ++s)
         if (g->chk_order[s] == check) { slot = (int32_t)s; break; }

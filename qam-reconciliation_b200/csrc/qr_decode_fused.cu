@@ -28,7 +28,6 @@ namespace cg = cooperative_groups;
 namespace qr {
 
 constexpr int kFBlock = 256;
-[[maybe_unused]] constexpr int kFusedRowsPerClaim = 4;   // checks per thread and claim
 constexpr int kFusedMaxTile = 128;
 
 __device__ __forceinline__ uint64_t l2_policy(int kind)
@@ -40,49 +39,6 @@ __device__ __forceinline__ uint64_t l2_policy(int kind)
     return p;
 }
 
-// per-lane "some check unsatisfied" bits of this CTA's threads -> one global store per lane
-template <int VEC>
-__device__ __forceinline__ void flush_bad(int32_t *unsat_cur, int32_t lane0, int32_t tx, int32_t ty, int32_t tl,
-                                          uint32_t bad, int32_t *s_flags)
-{
-    for (int32_t i = threadIdx.x; i < tl; i += blockDim.x) s_flags[i] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < VEC; ++k)
-        if (bad >> k & 1) s_flags[tx * VEC + k] = 1;
-    __syncthreads();
-    if (ty == 0) {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k)
-            if (s_flags[tx * VEC + k]) unsat_cur[lane0 + tx * VEC + k] = 1;
-    }
-    __syncthreads();
-}
-
-// The gathers of a tile touch its rows in random order; left to them, the first touch of every row is a DRAM
-// round trip that a thread waits for with its registers tied up.  Instead, whoever takes claim `chunk` of a
-// tile pulls the SAME chunk of the NEXT tile into L2 in address order (prefetch.global.L2 holds no register
-// and no scoreboard): DRAM sees long sequential bursts one tile ahead of the sweep, the gathers hit L2.
-template <typename T>
-__device__ __forceinline__ void prefetch_next_tile(const FusedParams<T> &F, int cur, int32_t tile, int32_t chunk,
-                                                   int32_t cpt, int32_t c0, int32_t c1, int32_t deg_slots0,
-                                                   int32_t deg_slots1)
-{
-    const DecodeParams<T> &P = F.P;
-    const bool wrap = tile + 1 >= F.tiles;            // the next sweep starts over on the other buffer
-    const int32_t pt = wrap ? 0 : tile + 1;
-    const char *pc = reinterpret_cast<const char *>(F.c2v[wrap ? (cur ^ 1) : cur] + ((int64_t)pt * P.E + deg_slots0) * F.tl);
-    const int64_t cbytes = (int64_t)(deg_slots1 - deg_slots0) * F.tl * (int64_t)sizeof(T);
-    for (int64_t o = (int64_t)threadIdx.x * 128; o < cbytes; o += (int64_t)kFBlock * 128)
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(pc + o));
-    const int64_t v0 = P.N * chunk / cpt, v1 = P.N * (chunk + 1) / cpt;
-    const char *pl = reinterpret_cast<const char *>(P.llr + ((int64_t)pt * P.N + v0) * F.tl);
-    const int64_t lbytes = (v1 - v0) * F.tl * (int64_t)sizeof(T);
-    for (int64_t o = (int64_t)threadIdx.x * 128; o < lbytes; o += (int64_t)kFBlock * 128)
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(pl + o));
-    (void)c0; (void)c1;
-}
-
 // Work distribution: WARPS claim work, not CTAs.  A warp is 32 / bx checks wide (bx = TL / VEC threads share a
 // check) and takes rows_per_claim passes per claim from one global counter, in tile order; the atomic of the
 // NEXT claim is issued before the current one is processed.  No CTA barrier inside the phase, so the warps of
@@ -90,10 +46,8 @@ __device__ __forceinline__ void prefetch_next_tile(const FusedParams<T> &F, int 
 // 2.1 us per claim, profiles/r1_fused_experiments.txt f7/f8).  Per-lane "some check unsatisfied" flags are
 // OR-reduced inside the warp and stored per tile (idempotent stores of 1).
 template <typename T, int VEC, int DSEL>
-__device__ __forceinline__ void fused_phase(const FusedParams<T> &F, int cur, int32_t *s_flags, int32_t *s_claim,
-                                            uint64_t pol_ld, uint64_t pol_st)
+__device__ __forceinline__ void fused_phase(const FusedParams<T> &F, int cur, uint64_t pol_ld, uint64_t pol_st)
 {
-    (void)s_flags; (void)s_claim;
     const DecodeParams<T> &P = F.P;
     const int32_t bx = F.tl / VEC;                    // threads per check row (<= 32)
     const int32_t lane = threadIdx.x & 31;
@@ -153,373 +107,6 @@ __device__ __forceinline__ void fused_phase(const FusedParams<T> &F, int cur, in
         if (dyn) nxt = __shfl_sync(0xffffffffu, nxt, 0);
     }
     if (tile_prev >= 0) flush();
-}
-
-// ---------------------------------------------------------------------------------------------
-// PIPELINED fused phase (check-regular graphs of degree D): the 4 D rows of an item go straight from L2
-// to a thread-private shared-memory slot with cp.async (no registers held while they fly), two items
-// deep -- while item k is being computed item k+1 is in flight, and item k+2 is issued as soon as k's
-// slot is free.  Per SM 2 x 256 x 4 D x 16 B (192 KB for D = 6) of loads can be outstanding, against
-// the ~96 KB (and only between compute bursts) of the register-staged version.
-// Shared-memory slot of (stage s, row j) for thread t: uint4 index (s * 4 D + j) * kFBlock + t --
-// consecutive threads, consecutive 16 B: conflict-free LDS.128 / cp.async.
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint64_t pol)
-{
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "l"(pol)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-struct ItemMeta {
-    int32_t tile;      // tile of the claim this pipeline slot belongs to (the same for every thread of the CTA); -1: none
-    int32_t ci;        // internal check slot (row of the syndrome tile; first CSR slot = ci * D); -1: this thread has no item
-    uint32_t own;      // 2 bits per edge: position of the own edge among the variable's three
-    uint32_t sy;       // the VEC syndrome bytes of the thread's lanes
-    uint32_t active, fresh;
-};
-
-template <typename T, int VEC, int D, int STAGES>
-__device__ __forceinline__ void fused_phase_pipe(const FusedParams<T> &F, int cur, int32_t *s_flags,
-                                                 int32_t *s_claim, uint4 *stage, uint64_t pol_ld, uint64_t pol_st)
-{
-    using VT = Vec<T, VEC>;
-    constexpr int ROWS = 4 * D;
-    const DecodeParams<T> &P = F.P;
-    const int32_t tl = F.tl, bx = tl / VEC, by = kFBlock / bx;
-    const int32_t tx = threadIdx.x % bx, ty = threadIdx.x / bx, lt = tx * VEC;
-    const int32_t claim_rows = by * kFusedRowsPerClaim, C = (int32_t)P.C;
-    const int32_t cpt = (C + claim_rows - 1) / claim_rows, total = cpt * F.tiles;
-    const int64_t E = P.E, N = P.N;
-    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage + threadIdx.x);
-
-    // issue side: the claim being handed out row by row
-    int32_t cl_tile = -1, cl_c0 = 0, r = kFusedRowsPerClaim;
-    bool exhausted = false;
-    uint32_t L_active = 0, L_fresh = 0;
-    // compute side
-    ItemMeta meta0, meta1;   // (two named slots, selected at compile time: no local-memory array)
-    meta0.tile = meta1.tile = -1;
-    meta0.ci = meta1.ci = -1;
-    int32_t comp_tile = -1;
-    uint32_t bad = 0;
-
-    // item i of this thread; a new claim is fetched by the whole CTA at the same i
-    auto next_item = [&](ItemMeta &m, Nbr4 (&q)[D]) {
-        if (!exhausted && r == kFusedRowsPerClaim) {
-            __syncthreads();
-            if (threadIdx.x == 0) *s_claim = atomicAdd(&P.work[0], 1);
-            __syncthreads();
-            const int32_t cl = *s_claim;
-            if (cl >= total) {
-                exhausted = true;
-            } else {
-                const int32_t tile = cl / cpt;
-                cl_c0 = (cl - tile * cpt) * claim_rows;
-                r = 0;
-                if (tile != cl_tile) {
-                    const LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, (tile * tl) / VEC + tx);
-                    L_active = L.active; L_fresh = L.fresh;
-                    cl_tile = tile;
-                }
-                if (F.prefetch & 1) {
-                    // The gathers of a tile touch its rows in random order; left to them, the first touch of
-                    // every row is a random 128..256-byte DRAM access (row-buffer miss each time).  Instead the
-                    // SAME chunk of the NEXT tile is pulled into L2 here in address order, one claim ahead of
-                    // the sweep: DRAM sees long sequential bursts, the gathers hit L2.
-                    const int32_t chunk = cl - tile * cpt;
-                    const bool wrap = tile + 1 >= F.tiles;            // next sweep starts over on the other buffer
-                    const int32_t pt = wrap ? 0 : tile + 1;
-                    const T *pc = F.c2v[wrap ? (cur ^ 1) : cur] + ((int64_t)pt * E + (int64_t)cl_c0 * D) * tl;
-                    const int32_t c_hi = min(cl_c0 + claim_rows, C);
-                    const int64_t cbytes = (int64_t)(c_hi - cl_c0) * D * tl * (int64_t)sizeof(T);
-                    for (int64_t o = (int64_t)threadIdx.x * 128; o < cbytes; o += (int64_t)kFBlock * 128)
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char *>(pc) + o));
-                    const int64_t v0 = N * chunk / cpt, v1 = N * (chunk + 1) / cpt;
-                    const T *pl = P.llr + ((int64_t)pt * N + v0) * tl;
-                    const int64_t lbytes = (v1 - v0) * tl * (int64_t)sizeof(T);
-                    for (int64_t o = (int64_t)threadIdx.x * 128; o < lbytes; o += (int64_t)kFBlock * 128)
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char *>(pl) + o));
-                }
-            }
-        }
-        m.tile = -1; m.ci = -1; m.own = 0; m.sy = 0; m.active = 0; m.fresh = 0;
-        if (!exhausted) {
-            const int32_t row = cl_c0 + ty + r * by;
-            ++r;
-            m.tile = cl_tile;
-            if (row < C && L_active) {
-                m.ci = row; m.active = L_active; m.fresh = L_fresh;
-                load_nbr_row<D>(F.nbr, row * D, q);
-                const uint8_t *sp = P.synd + ((int64_t)cl_tile * C + row) * tl + lt;
-                if constexpr (VEC == 4) m.sy = *reinterpret_cast<const uint32_t *>(sp);
-                else m.sy = *reinterpret_cast<const uint16_t *>(sp);
-#pragma unroll
-                for (int e = 0; e < D; ++e) m.own |= ((uint32_t)q[e].vp >> 28) << (2 * e);
-            }
-        }
-    };
-    // the rows of item `c` have landed in stage s
-    auto compute = [&](const ItemMeta &c, int s) {
-        if (c.tile != comp_tile) {      // CTA-uniform: publish the flags of the tile just finished
-            if (comp_tile >= 0) flush_bad<VEC>(P.unsat[cur], comp_tile * tl, tx, ty, tl, bad, s_flags);
-            bad = 0;
-            comp_tile = c.tile;
-        }
-        if (c.ci < 0) return;
-        T *c_new = F.c2v[cur ^ 1] + (int64_t)c.tile * E * tl + lt;
-        uint32_t par = 0;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) par |= ((c.sy >> (8 * k)) & 1u) << k;
-        VT x[D];
-#pragma unroll
-        for (int e = 0; e < D; ++e) {
-            VT ch, m0, m1, m2;
-            const uint4 *sp = stage + ((size_t)(s * ROWS + 4 * e) * kFBlock + threadIdx.x);
-            const uint4 t0 = sp[0], t1 = sp[kFBlock], t2 = sp[2 * kFBlock], t3 = sp[3 * kFBlock];
-            memcpy(&ch, &t0, 16); memcpy(&m0, &t1, 16); memcpy(&m1, &t2, 16); memcpy(&m2, &t3, 16);
-            const int own = (int)((c.own >> (2 * e)) & 3u);
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                const bool fresh = (c.fresh >> k & 1) != 0;          // first half-iteration: c2v == 0 (decoder.pyx:408)
-                const T c0 = fresh ? (T)0 : m0.v[k];
-                const T c1 = fresh ? (T)0 : m1.v[k];
-                const T c2 = fresh ? (T)0 : m2.v[k];
-                T post = ch.v[k] + c0;                               // decoder.pyx:291-293, ascending edge id
-                post = post + c1;
-                post = post + c2;
-                par ^= (uint32_t)(post < (T)0) << k;                 // decoder.pyx:244 (strict <)
-                const T mine = own == 0 ? c0 : (own == 1 ? c1 : c2);
-                x[e].v[k] = post - mine;                             // decoder.pyx:295-297
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            T xs[D];
-#pragma unroll
-            for (int e = 0; e < D; ++e) xs[e] = x[e].v[k];
-            MathOf<T>::template run<D, D>(D, xs, ((c.sy >> (8 * k)) & 1u) != 0);
-#pragma unroll
-            for (int e = 0; e < D; ++e) x[e].v[k] = xs[e];
-        }
-#pragma unroll
-        for (int e = 0; e < D; ++e)
-            st_pol(reinterpret_cast<VT *>(c_new + ((int64_t)c.ci * D + e) * tl), x[e], pol_st);
-        bad |= par & c.active;
-    };
-    auto issue = [&](const ItemMeta &m, const Nbr4 (&q)[D], int s) {
-        if (m.ci >= 0) {
-            const T *c_old = F.c2v[cur] + (int64_t)m.tile * E * tl + lt;
-            const T *llr_t = P.llr + (int64_t)m.tile * N * tl + lt;
-#pragma unroll
-            for (int e = 0; e < D; ++e) {
-                const uint32_t dst = stage_base + (uint32_t)((s * ROWS + 4 * e) * kFBlock * 16);
-                cp_async16(dst, llr_t + (int64_t)(q[e].vp & 0x0fffffff) * tl, pol_ld);
-                cp_async16(dst + kFBlock * 16, c_old + (int64_t)q[e].n0 * tl, pol_ld);
-                cp_async16(dst + 2 * kFBlock * 16, c_old + (int64_t)q[e].n1 * tl, pol_ld);
-                cp_async16(dst + 3 * kFBlock * 16, c_old + (int64_t)q[e].n2 * tl, pol_ld);
-            }
-        }
-        cp_async_commit();
-    };
-
-    if constexpr (STAGES == 1) {
-        // one item per thread in flight; latency is covered by the other warps of the SM (2 CTAs resident)
-        for (;;) {
-            ItemMeta m;
-            Nbr4 q[D];
-            next_item(m, q);
-            if (exhausted) break;
-            issue(m, q, 0);
-            cp_async_wait0();
-            compute(m, 0);
-        }
-    } else {
-        // two items deep: compute i - 2, then refill its stage with item i
-        auto step = [&](auto S) -> bool {
-            constexpr int s = decltype(S)::value;
-            ItemMeta &slot = s ? meta1 : meta0;
-            ItemMeta m;
-            Nbr4 q[D];
-            next_item(m, q);
-            const ItemMeta c = slot;
-            cp_async_wait1();
-            compute(c, s);
-            issue(m, q, s);
-            slot = m;
-            return exhausted && meta0.tile < 0 && meta1.tile < 0;
-        };
-        for (;;) {
-            if (step(std::integral_constant<int, 0>{})) break;
-            if (step(std::integral_constant<int, 1>{})) break;
-        }
-        cp_async_wait0();
-    }
-    if (comp_tile >= 0) flush_bad<VEC>(P.unsat[cur], comp_tile * tl, tx, ty, tl, bad, s_flags);
-}
-
-// ---------------------------------------------------------------------------------------------
-// BULK-COPY fused phase (PIPE == 3): the bx threads that share a check (one lane-tile row each) stage the
-// 4 D rows of their item with TMA bulk copies (cp.async.bulk, one whole TL * w byte row per copy, completion
-// on the group's mbarrier) instead of per-thread 16-byte cp.async -- measured on B200, per-thread 16-byte
-// cp.async.cg requests are NOT merged into shared sectors (every thread pulls its own 32-byte sector: twice
-// the L2 -> SM traffic, profiles/r1_fused_*), whole-row bulk copies move exactly the row.
-// Stage of group g: smem[g][4 D rows][TL * w bytes]; thread tx reads bytes [16 tx, 16 tx + 16) of each row.
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_row(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
-}
-
-template <typename T, int VEC, int D>
-__device__ __forceinline__ void fused_phase_bulk(const FusedParams<T> &F, int cur, int32_t *s_flags,
-                                                 int32_t *s_claim, unsigned char *stage, uint64_t *bars,
-                                                 uint32_t &phase, uint64_t pol_ld, uint64_t pol_st)
-{
-    using VT = Vec<T, VEC>;
-    constexpr int ROWS = 4 * D;
-    const DecodeParams<T> &P = F.P;
-    const int32_t tl = F.tl, bx = tl / VEC, by = kFBlock / bx;
-    const int32_t tx = threadIdx.x % bx, ty = threadIdx.x / bx, lt = tx * VEC;
-    const int32_t claim_rows = by * kFusedRowsPerClaim, C = (int32_t)P.C;
-    const int32_t cpt = (C + claim_rows - 1) / claim_rows, total = cpt * F.tiles;
-    const int64_t E = P.E, N = P.N;
-    const uint32_t row_bytes = (uint32_t)(tl * sizeof(T));
-    unsigned char *my_stage = stage + (size_t)ty * ROWS * row_bytes;
-    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(my_stage);
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bars + ty);
-    // lanes of the warp that belong to this thread's group (bx <= 32 consecutive lanes)
-    const uint32_t lane_id = threadIdx.x & 31u;
-    const uint32_t grp_mask = (bx >= 32 ? 0xffffffffu : ((1u << bx) - 1u) << (lane_id / bx * bx));
-
-    int32_t cl_tile = -1, cl_c0 = 0, r = kFusedRowsPerClaim;
-    bool exhausted = false;
-    uint32_t L_active = 0, L_fresh = 0;
-    int32_t comp_tile = -1;
-    uint32_t bad = 0;
-
-    for (;;) {
-        if (r == kFusedRowsPerClaim) {
-            __syncthreads();
-            if (threadIdx.x == 0) *s_claim = atomicAdd(&P.work[0], 1);
-            __syncthreads();
-            const int32_t cl = *s_claim;
-            if (cl >= total) {
-                exhausted = true;
-            } else {
-                const int32_t tile = cl / cpt;
-                cl_c0 = (cl - tile * cpt) * claim_rows;
-                r = 0;
-                if (tile != cl_tile) {
-                    const LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, (tile * tl) / VEC + tx);
-                    L_active = L.active; L_fresh = L.fresh;
-                    cl_tile = tile;
-                }
-            }
-        }
-        if (exhausted) break;
-        const int32_t row = cl_c0 + ty + r * by;
-        ++r;
-        if (cl_tile != comp_tile) {      // CTA-uniform: publish the flags of the tile just finished
-            if (comp_tile >= 0) flush_bad<VEC>(P.unsat[cur], comp_tile * tl, tx, ty, tl, bad, s_flags);
-            bad = 0;
-            comp_tile = cl_tile;
-        }
-        // the group has an item if its check exists and any of its lanes runs a frame
-        const bool grp_valid = row < C && (__ballot_sync(0xffffffffu, L_active != 0) & grp_mask) != 0;
-        Nbr4 q[D];
-        uint32_t own = 0, sy = 0;
-        if (grp_valid) {
-            load_nbr_row<D>(F.nbr, row * D, q);
-            const uint8_t *sp = P.synd + ((int64_t)cl_tile * C + row) * tl + lt;
-            if constexpr (VEC == 4) sy = *reinterpret_cast<const uint32_t *>(sp);
-            else sy = *reinterpret_cast<const uint16_t *>(sp);
-        }
-        __syncwarp();                   // everyone is done reading the stage of the previous item
-        if (grp_valid && tx == 0) mbar_expect_tx(bar, ROWS * row_bytes);
-        __syncwarp();
-        if (grp_valid) {
-            const char *c_old = reinterpret_cast<const char *>(F.c2v[cur] + (int64_t)cl_tile * E * tl);
-            const char *llr_t = reinterpret_cast<const char *>(P.llr + (int64_t)cl_tile * N * tl);
-#pragma unroll
-            for (int e = 0; e < D; ++e) {
-                own |= ((uint32_t)q[e].vp >> 28) << (2 * e);
-                // row j = 4 e + {0: llr, 1..3: the variable's three messages}; thread tx issues rows j % bx == tx
-                const int32_t idx[4] = {q[e].vp & 0x0fffffff, q[e].n0, q[e].n1, q[e].n2};
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int j = 4 * e + jj;
-                    if ((j & (bx - 1)) == tx)
-                        bulk_row(stage_addr + j * row_bytes, (jj == 0 ? llr_t : c_old) + (int64_t)idx[jj] * row_bytes,
-                                 row_bytes, bar, pol_ld);
-                }
-            }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-        }
-        if (grp_valid && L_active) {
-            T *c_new = F.c2v[cur ^ 1] + (int64_t)cl_tile * E * tl + lt;
-            uint32_t par = 0;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) par |= ((sy >> (8 * k)) & 1u) << k;
-            VT x[D];
-#pragma unroll
-            for (int e = 0; e < D; ++e) {
-                VT ch, m0, m1, m2;
-                const unsigned char *sp = my_stage + (size_t)(4 * e) * row_bytes + tx * 16;
-                const uint4 t0 = *reinterpret_cast<const uint4 *>(sp);
-                const uint4 t1 = *reinterpret_cast<const uint4 *>(sp + row_bytes);
-                const uint4 t2 = *reinterpret_cast<const uint4 *>(sp + 2 * row_bytes);
-                const uint4 t3 = *reinterpret_cast<const uint4 *>(sp + 3 * row_bytes);
-                memcpy(&ch, &t0, 16); memcpy(&m0, &t1, 16); memcpy(&m1, &t2, 16); memcpy(&m2, &t3, 16);
-                const int ow = (int)((own >> (2 * e)) & 3u);
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) {
-                    const bool fresh = (L_fresh >> k & 1) != 0;          // first half-iteration: c2v == 0 (decoder.pyx:408)
-                    const T c0 = fresh ? (T)0 : m0.v[k];
-                    const T c1 = fresh ? (T)0 : m1.v[k];
-                    const T c2 = fresh ? (T)0 : m2.v[k];
-                    T post = ch.v[k] + c0;                               // decoder.pyx:291-293, ascending edge id
-                    post = post + c1;
-                    post = post + c2;
-                    par ^= (uint32_t)(post < (T)0) << k;                 // decoder.pyx:244 (strict <)
-                    const T mine = ow == 0 ? c0 : (ow == 1 ? c1 : c2);
-                    x[e].v[k] = post - mine;                             // decoder.pyx:295-297
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                T xs[D];
-#pragma unroll
-                for (int e = 0; e < D; ++e) xs[e] = x[e].v[k];
-                MathOf<T>::template run<D, D>(D, xs, ((sy >> (8 * k)) & 1u) != 0);
-#pragma unroll
-                for (int e = 0; e < D; ++e) x[e].v[k] = xs[e];
-            }
-#pragma unroll
-            for (int e = 0; e < D; ++e)
-                st_pol(reinterpret_cast<VT *>(c_new + ((int64_t)row * D + e) * tl), x[e], pol_st);
-            bad |= par & L_active;
-        }
-    }
-    if (comp_tile >= 0) flush_bad<VEC>(P.unsat[cur], comp_tile * tl, tx, ty, tl, bad, s_flags);
 }
 
 // REFILL PHASE of the fused schedule.  `buf` = lane-state buffer (and refill list) the bookkeeping of this
@@ -632,31 +219,18 @@ __device__ __forceinline__ void fused_refill_phase(const FusedParams<T> &F, int 
     }
 }
 
-template <typename T, int VEC, int DSEL, int PIPE>   // PIPE: 0 register-staged, 1 / 2 = cp.async stages per thread
-__global__ void __launch_bounds__(kFBlock, (PIPE == 1 || (PIPE == 3 && sizeof(T) == 4) || (PIPE == 0 && DSEL > 0)) ? ((sizeof(T) == 4 && VEC == 2) ? 3 : 2) : 1) k_fused(FusedParams<T> F)
+template <typename T, int VEC, int DSEL>
+__global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(FusedParams<T> F)
 {
-    extern __shared__ uint4 dyn_stage[];   // PIPE stages x 4 DSEL rows x kFBlock threads x 16 B
-    __shared__ uint64_t s_bars[kFBlock / 2];   // PIPE == 3: one mbarrier per group of bx threads
-    uint32_t bulk_phase = 0;
-    __shared__ int32_t s_flags[kFusedMaxTile];
-    __shared__ int32_t s_claim[2], s_last;
+    __shared__ int32_t s_last;
     const DecodeParams<T> &P = F.P;
     cg::grid_group grid = cg::this_grid();
     const uint64_t pol_ld = l2_policy(F.hints >= 2 ? 2 : 0), pol_st = l2_policy(F.hints >= 1 ? 1 : 0);
-    if constexpr (PIPE == 3) {
-        if (threadIdx.x < kFBlock / 2) mbar_init((uint32_t)__cvta_generic_to_shared(s_bars + threadIdx.x), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        __syncthreads();
-    }
     fused_refill_phase<T>(F, 0, 0);      // first generation of frames into the lanes
     grid.sync();
     for (int step = 0;; ++step) {
         const int cur = step & 1;
-        if constexpr (PIPE == 3)
-            fused_phase_bulk<T, VEC, DSEL>(F, cur, s_flags, s_claim, reinterpret_cast<unsigned char *>(dyn_stage), s_bars,
-                                           bulk_phase, pol_ld, pol_st);
-        else if constexpr (PIPE > 0) fused_phase_pipe<T, VEC, DSEL, PIPE>(F, cur, s_flags, s_claim, dyn_stage, pol_ld, pol_st);
-        else fused_phase<T, VEC, DSEL>(F, cur, s_flags, s_claim, pol_ld, pol_st);
+        fused_phase<T, VEC, DSEL>(F, cur, pol_ld, pol_st);
         // the last CTA to get here advances the lane state machine (decoder.pyx:431-436) for every lane
         __threadfence();
         __syncthreads();
@@ -690,12 +264,11 @@ __global__ void __launch_bounds__(kFBlock, (PIPE == 1 || (PIPE == 3 && sizeof(T)
     }
 }
 
-template <typename T, int VEC, int DSEL, int PIPE>
+template <typename T, int VEC, int DSEL>
 static int launch_fused(qr_decoder *d, const FusedParams<T> &F, cudaStream_t stream)
 {
-    const size_t smem = (size_t)(PIPE == 3 ? 1 : PIPE) * 4 * DSEL * kFBlock * 16;
-    auto kern = k_fused<T, VEC, DSEL, PIPE>;
-    if (smem) QR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = 0;
+    auto kern = k_fused<T, VEC, DSEL>;
     int per_sm = 0;
     QR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFBlock, smem));
     if (per_sm < 1) return fail(QR_ERR_CUDA, "fused decoder kernel does not fit on an SM");
@@ -739,26 +312,13 @@ static int run_batch_fused_v(qr_decoder *d, const DecodeParams<T> &P, cudaStream
     F.prefetch = d->fused_prefetch;
     F.rows_per_claim = d->fused_rpc > 0 ? d->fused_rpc : 4;
     F.static_share = d->fused_static;
-#ifdef QR_FUSED_EXPERIMENTS
-    // staging variants measured on B200 and found slower than the register-staged phase:
-    // 1 / 2 = per-thread cp.async stages, 3 = TMA bulk copies of whole rows
-    if (d->regular_degree == 6 && d->fused_pipe == 3) return launch_fused<T, VEC, 6, 3>(d, F, stream);
-    if (d->regular_degree == 6 && d->fused_pipe == 2) return launch_fused<T, VEC, 6, 2>(d, F, stream);
-    if (d->regular_degree == 6 && d->fused_pipe == 1 && sizeof(T) == 4) return launch_fused<T, VEC, 6, 1>(d, F, stream);
-#endif
-    if (d->regular_degree == 6) return launch_fused<T, VEC, 6, 0>(d, F, stream);
-    return launch_fused<T, VEC, 0, 0>(d, F, stream);
+    if (d->regular_degree == 6) return launch_fused<T, VEC, 6>(d, F, stream);
+    return launch_fused<T, VEC, 0>(d, F, stream);
 }
 
 template <typename T>
 int run_batch_fused(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream)
 {
-#ifdef QR_FUSED_EXPERIMENTS
-    // 2 lanes per thread (8-byte accesses, 80 registers, 3 CTAs/SM = 24 warps): measured 69.6 ms against 61.7 ms
-    if constexpr (sizeof(T) == 4) {
-        if (d->vec == 2 && d->regular_degree == 6) return run_batch_fused_v<T, 2>(d, P, stream);   // QAMRECON_VEC=2
-    }
-#endif
     return run_batch_fused_v<T, 16 / sizeof(T)>(d, P, stream);
 }
 

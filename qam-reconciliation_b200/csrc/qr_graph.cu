@@ -28,6 +28,8 @@ int fail(int code, const std::string &msg)
 
 const char *last_error() { return g_last_error.c_str(); }
 
+bool fused_eligible(const qr_graph *g);   // qr_decode_fused.cu
+
 template <typename T>
 static int upload(T **dst, const std::vector<T> &src)
 {
@@ -58,8 +60,30 @@ int qr_device_count(int *count)
     return QR_OK;
 }
 
+static int graph_create(const int64_t *h_vid, const int64_t *h_cid, int64_t n_edges, int device, bool strict,
+                        qr_graph **out);
+
 int qr_graph_create(const int64_t *h_vid, const int64_t *h_cid, int64_t n_edges, int device,
                     qr_graph **out)
+{
+    return graph_create(h_vid, h_cid, n_edges, device, true, out);
+}
+
+int qr_graph_create_any(const int64_t *h_vid, const int64_t *h_cid, int64_t n_edges, int device,
+                        qr_graph **out)
+{
+    return graph_create(h_vid, h_cid, n_edges, device, false, out);
+}
+
+int qr_graph_fused_eligible(const qr_graph *g, int *eligible)
+{
+    if (!g || !eligible) return qr::fail(QR_ERR_INVALID, "null pointer");
+    *eligible = qr::fused_eligible(g) ? 1 : 0;
+    return QR_OK;
+}
+
+static int graph_create(const int64_t *h_vid, const int64_t *h_cid, int64_t n_edges, int device, bool strict,
+                        qr_graph **out)
 {
     if (!out) return qr::fail(QR_ERR_INVALID, "null output pointer");
     *out = nullptr;
@@ -67,7 +91,7 @@ int qr_graph_create(const int64_t *h_vid, const int64_t *h_cid, int64_t n_edges,
     if (!g) return qr::fail(QR_ERR_NOMEM, "out of host memory");
     int rc;
     try {
-        rc = qr::build_host_tables(*g, h_vid, h_cid, n_edges);
+        rc = qr::build_host_tables(*g, h_vid, h_cid, n_edges, strict);
     } catch (const std::bad_alloc &) {
         rc = qr::fail(QR_ERR_NOMEM, "out of host memory building the graph tables");
     }

@@ -8,7 +8,10 @@
 
 namespace qr {
 
-inline int build_host_tables(qr_graph &g, const int64_t *vid, const int64_t *cid, int64_t E)
+// strict: the decoder's requirements (every check of degree 2..kMaxCheckDegree) are enforced here, as
+// Decoder.__cinit__ would have to; !strict (Matrix: any edge list, matrix.pyx:21-38 accepts checks of any degree,
+// unused check ids included) only records whether the graph is decodable.
+inline int build_host_tables(qr_graph &g, const int64_t *vid, const int64_t *cid, int64_t E, bool strict = true)
 {
     if (!vid || !cid) return fail(QR_ERR_INVALID, "null edge array");
     if (E <= 0) return fail(QR_ERR_GRAPH, "edge list is empty");
@@ -28,7 +31,9 @@ inline int build_host_tables(qr_graph &g, const int64_t *vid, const int64_t *cid
     g.max_cdeg = *std::max_element(cdeg.begin(), cdeg.end());
     g.max_vdeg = *std::max_element(vdeg.begin(), vdeg.end());
     g.var_deg = (*std::min_element(vdeg.begin(), vdeg.end()) == g.max_vdeg) ? g.max_vdeg : 0;
-    for (int64_t c = 0; c < C; ++c) {
+    g.decodable = g.max_cdeg <= kMaxCheckDegree;
+    for (int64_t c = 0; c < C; ++c) g.decodable = g.decodable && cdeg[c] >= 2;
+    for (int64_t c = 0; strict && c < C; ++c) {
         // the reference indexes its 2*(deg-1) scratch out of bounds for degree 1 and dereferences a
         // failed malloc for degree 0 (decoder.pyx:131-135, :337-342): reject instead
         if (cdeg[c] < 2) {
@@ -38,7 +43,7 @@ inline int build_host_tables(qr_graph &g, const int64_t *vid, const int64_t *cid
             return fail(QR_ERR_GRAPH, b);
         }
     }
-    if (g.max_cdeg > kMaxCheckDegree) {
+    if (strict && g.max_cdeg > kMaxCheckDegree) {
         char b[160];
         snprintf(b, sizeof(b), "check degree %d exceeds the supported maximum %d", g.max_cdeg,
                  kMaxCheckDegree);

@@ -69,6 +69,7 @@ struct qr_mapper {
     double noise_var = 0, sigma = 0, s2 = 0;
     double *d_tables = nullptr;  // one allocation holding every table below
     uint8_t *d_sign = nullptr;
+    int32_t *d_index_errors = nullptr;   // see MapperView::index_errors
     uint8_t *d_sign_g = nullptr;   // sign rule of g / g_inv / map_noise (differs from d_sign only for the FlipSign subclasses)
     double *grid_y = nullptr, *grid_F = nullptr;   // dense F_Y grid of noisemapper.pyx:135-144 (one allocation), built on demand
     int32_t grid_n = 0;

@@ -21,6 +21,7 @@ static MapperView view_of(const qr_mapper *m)
     v.inv_tab = m->inv_tab; v.inv_pdf = m->inv_pdf; v.inv_n = m->inv_n; v.inv_y0 = m->inv_y0; v.inv_h = m->inv_h;
     v.inv_jump = m->inv_jump; v.inv_jn = m->inv_jn;
     v.uniform = m->uniform;
+    v.index_errors = m->d_index_errors;
     return v;
 }
 
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(256) k_front_end(MapperView m, const double *_
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
          j += (int64_t)gridDim.x * blockDim.x) {
         int32_t i;
-        if (idx_in) i = (int32_t)idx_in[j];
+        if (idx_in) i = checked_index(m, idx_in[j]);
         else i = hard_decide(s.thr, m.order, y[j]);
         if (idx_out) idx_out[j] = i;
         if (n_hat) {
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(128) k_demap(MapperView m, const double *__res
     for (int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sidx < n;
          sidx += (int64_t)gridDim.x * blockDim.x) {
         double out[kMaxBps];
-        demap_symbol(m, t, n_hat[sidx], (int32_t)tx[sidx], mode, alpha, out);
+        demap_symbol(m, t, n_hat[sidx], checked_index(m, tx[sidx]), mode, alpha, out);
         for (int k = 0; k < m.bps; ++k) llr[sidx * m.bps + k] = (OUT)out[k];
     }
 }
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(128) k_g_inv(MapperView m, const double *__res
     stage_tables(m, s);
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
          j += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t i = (int32_t)region[j];
+        const int32_t i = checked_index(m, region[j]);
         const double target = inv_target(s.sign, s.FYt, s.delta, n_hat[j], i);
         y_hat[j] = (mode & 1) ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i, InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h, m.inv_jump, m.inv_jn})
                               : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) k_bare_llr(MapperView m, const long long 
 {
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
          j += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t i = (int32_t)tx[j];
+        const int32_t i = checked_index(m, tx[j]);
         for (int k = 0; k < m.bps; ++k) llr[j * m.bps + k] = (OUT)m.bare[i * m.bps + k];
     }
 }
@@ -214,6 +215,8 @@ int qr_mapper_create(int bits_per_symbol, const double *h_constellation, const d
         QR_CUDA_CHECK(cudaMalloc((void **)&m->d_tables, nd * sizeof(double)));
         QR_CUDA_CHECK(cudaMalloc((void **)&m->d_sign, M));
         QR_CUDA_CHECK(cudaMalloc((void **)&m->d_sign_g, M));
+        QR_CUDA_CHECK(cudaMalloc((void **)&m->d_index_errors, sizeof(int32_t)));
+        QR_CUDA_CHECK(cudaMemset(m->d_index_errors, 0, sizeof(int32_t)));
         double *p = m->d_tables;
         m->constellation = p; p += M;
         m->thresholds = p; p += M + 1;
@@ -265,11 +268,28 @@ void qr_mapper_destroy(qr_mapper *m)
         cudaFree(m->d_tables);
         cudaFree(m->d_sign);
         cudaFree(m->d_sign_g);
+        cudaFree(m->d_index_errors);
         cudaFree(m->grid_y);
         cudaFree(m->inv_tab);
         cudaFree(m->inv_jump);
     }
     delete m;
+}
+
+int qr_mapper_index_errors(qr_mapper *m, int64_t *count, void *stream)
+{
+    if (!m || !count) return qr::fail(QR_ERR_INVALID, "null pointer");
+    qr::DeviceGuard guard(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t h = 0;
+    QR_CUDA_CHECK(cudaMemcpyAsync(&h, m->d_index_errors, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    QR_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h) {
+        QR_CUDA_CHECK(cudaMemsetAsync(m->d_index_errors, 0, sizeof(int32_t), st));
+        QR_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    *count = h;
+    return QR_OK;
 }
 
 int qr_mapper_tables(const qr_mapper *m, double *F_Y_thresholds, double *delta_F_Y, double *fwrd,

@@ -33,7 +33,22 @@ struct MapperView {
     const int32_t *inv_jump;      // see InvTable::jump
     int32_t inv_jn;
     int32_t uniform;              // constellation points equally spaced (always true for PAMAlphabet): enables E^m G[m]
+    int32_t *index_errors;        // device counter of caller-supplied symbol / region indices found out of range
 };
+
+// Caller-supplied symbol / region index -> [0, order): the reference's bounds-checked Cython raises IndexError
+// for anything else; a kernel cannot raise, so it counts the offence (read back by qr_mapper_index_errors, which
+// the Python classes turn into IndexError) and computes on index 0 instead of reading out of bounds.
+QR_HD int32_t checked_index(const MapperView &m, long long idx)
+{
+    if (idx >= 0 && idx < (long long)m.order) return (int32_t)idx;
+#if defined(__CUDA_ARCH__)
+    if (m.index_errors) atomicAdd(m.index_errors, 1);
+#else
+    if (m.index_errors) ++*m.index_errors;
+#endif
+    return 0;
+}
 
 struct InvTable {
     const double *F;   // F_Y at y0 + j*h

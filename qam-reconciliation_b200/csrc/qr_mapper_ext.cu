@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(128) k_demap_noise(MapperView m, const uint8_t
     for (int i = threadIdx.x; i < m.order; i += blockDim.x) sg[i] = sign_g[i];
     __syncthreads();
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
-        y_hat[j] = g_inv_grid(s, sg, gF, gy, npts, n_hat[j], (int32_t)symb[j]);
+        y_hat[j] = g_inv_grid(s, sg, gF, gy, npts, n_hat[j], checked_index(m, symb[j]));
 }
 
 // variant 1: demap_lappr_simplified (noisemapper.pyx:563-601); variant 2: demap_lappr_sofisticated (:624-748)
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) k_demap_variant(MapperView m, const uint8
     const double two_s2 = 2 * m.noise_var;
     for (int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sidx < n;
          sidx += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t j = (int32_t)tx[sidx];
+        const int32_t j = checked_index(m, tx[sidx]);
         const double nv = n_hat[sidx], a_j = s.a[j];
         double N[kMaxBps], D[kMaxBps];
         for (int k = 0; k < bps; ++k) { N[k] = 0; D[k] = 0; }
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128) k_information(MapperView m, const uint8_t
     const double two_s2 = 2.0 * m.noise_var;
     double I0 = 0, I1 = 0, I2 = 0;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t xi = (int32_t)x_ind[j];
+        const int32_t xi = checked_index(m, x_ind[j]);
         const double yv = y[j], x = s.a[xi];
         const int32_t xh = hard_decide(s.thr, M, yv);                                   // :241
         const double F = mixture_cdf(s.a, s.p, M, m.s2, yv);                            // :242 (g)

@@ -227,7 +227,11 @@ extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, in
         int rc = run_chain(d, m, mode, demap_mode, alpha, b.y, b.tx, nf, S, max_iterations, k_info, b.n_hat, b.word,
                            b.synd, b.llr, llr_dtype, b.success, b.iters, b.post, post_dtype,
                            h_bit_errors ? b.errors : nullptr, st);
-        if (rc) return rc;
+        if (rc) {
+            // copies of this and earlier chunks may still be in flight into / out of caller memory
+            cudaStreamSynchronize(d->s_in); cudaStreamSynchronize(st); cudaStreamSynchronize(d->s_out);
+            return rc;
+        }
         QR_CUDA_CHECK(cudaEventRecord(d->ev_compute[s], st));
         // stage 3: results of chunk c
         QR_CUDA_CHECK(cudaStreamWaitEvent(d->s_out, d->ev_compute[s], 0));

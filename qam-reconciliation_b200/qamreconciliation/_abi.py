@@ -24,6 +24,8 @@ SIGNATURES = {
     "qr_last_error": (C.c_char_p, []),
     "qr_device_count": (C.c_int, [_P(C.c_int)]),
     "qr_graph_create": (C.c_int, [_vp, _vp, _i64, C.c_int, _P(_vp)]),
+    "qr_graph_create_any": (C.c_int, [_vp, _vp, _i64, C.c_int, _P(_vp)]),
+    "qr_graph_fused_eligible": (C.c_int, [_vp, _P(C.c_int)]),
     "qr_graph_destroy": (None, [_vp]),
     "qr_graph_info": (C.c_int, [_vp, _P(_i64), _P(_i64), _P(_i64), _P(_i32), _P(_i32)]),
     "qr_graph_export": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -41,6 +43,7 @@ SIGNATURES = {
     "qr_check_synd_node": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "qr_mapper_create": (C.c_int, [C.c_int, _vp, _vp, _vp, _f64, _vp, C.c_int, _P(_vp)]),
     "qr_mapper_destroy": (None, [_vp]),
+    "qr_mapper_index_errors": (C.c_int, [_vp, _P(_i64), _vp]),
     "qr_mapper_tables": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qr_hard_decide_index": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "qr_symbols_to_bits": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),

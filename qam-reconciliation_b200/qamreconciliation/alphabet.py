@@ -96,4 +96,9 @@ class PAMAlphabet(Alphabet):
     def demap_symbols_to_bits(self, symbol_index):
         """alphabet.pyx:98-107: bits[i*bps + k] = s_to_b[index[i], k]; returns a uint8 numpy array."""
         idx = to_dev(symbol_index, torch.int64).reshape(-1)
-        return to_np(self.demap_symbols_to_bits_batch(idx))
+        out = to_np(self.demap_symbols_to_bits_batch(idx))
+        n = C.c_int64()
+        _abi.check(_abi.lib().qr_mapper_index_errors(self._handle(), C.byref(n), stream()))
+        if n.value:     # the reference's bounds-checked table lookup raises
+            raise IndexError(f"{n.value} symbol indices out of bounds for an alphabet of order {self.order}")
+        return out

@@ -47,6 +47,13 @@ class Decoder:
         """ Number of edges """
         return self._g.ednum
 
+    @property
+    def fused_eligible(self):
+        """True when the fused flooding-iteration schedule (QR_SCHED_FUSED) can run this graph."""
+        e = C.c_int()
+        _abi.check(_abi.lib().qr_graph_fused_eligible(self._g.h, C.byref(e)))
+        return bool(e.value)
+
     def __del__(self):
         for h in getattr(self, "_dec", {}).values():
             try:

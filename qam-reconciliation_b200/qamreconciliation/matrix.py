@@ -11,14 +11,15 @@ from ._util import device, stream, to_dev, to_np
 class _Graph:
     """Owns a qr_graph handle (CSR/CSC tables on the device)."""
 
-    def __init__(self, vid, cid):
+    def __init__(self, vid, cid, any_graph=False):
         vid = np.array(np.asarray(vid), dtype=np.int64, copy=True, order="C").ravel()
         cid = np.array(np.asarray(cid), dtype=np.int64, copy=True, order="C").ravel()
         if vid.shape[0] != cid.shape[0]:
             raise ValueError("Sizes don't match")
         dev = device()
         h = C.c_void_p()
-        _abi.check(_abi.lib().qr_graph_create(vid.ctypes.data, cid.ctypes.data, vid.size, dev.index, C.byref(h)))
+        create = _abi.lib().qr_graph_create_any if any_graph else _abi.lib().qr_graph_create
+        _abi.check(create(vid.ctypes.data, cid.ctypes.data, vid.size, dev.index, C.byref(h)))
         self.h = h
         self.device = dev
         n, c, e = C.c_int64(), C.c_int64(), C.c_int64()
@@ -43,7 +44,7 @@ class Matrix:
     def __init__(self, vnode_array, cnode_array):
         if np.asarray(vnode_array).shape[0] != np.asarray(cnode_array).shape[0]:
             raise ValueError("Incompatible sizes for input vectors")
-        self._g = _Graph(vnode_array, cnode_array)
+        self._g = _Graph(vnode_array, cnode_array, any_graph=True)   # the reference's Matrix takes any edge list
         self.vnum, self.cnum, self.ednum = self._g.vnum, self._g.cnum, self._g.ednum
 
     def eval_syndrome_batch(self, words):

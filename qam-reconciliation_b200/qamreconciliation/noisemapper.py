@@ -100,6 +100,21 @@ class NoiseMapper:
                 pass
             self._h = None
 
+    # -- caller-supplied symbol indices -----------------------------------------------------------
+    def check_indices(self):
+        """Raise IndexError (as the reference's bounds-checked Cython does) if any symbol / region index handed to
+        this mapper since the last check was outside [0, order).  Synchronises the current stream; the per-frame
+        (numpy) methods call it themselves, users of the `*_batch` methods call it when they next synchronise."""
+        n = C.c_int64()
+        _abi.check(_abi.lib().qr_mapper_index_errors(self._h, C.byref(n), stream()))
+        if n.value:
+            raise IndexError(f"{n.value} symbol indices out of bounds for an alphabet of order {self.order}")
+
+    def _np_checked(self, t):
+        out = to_np(t)
+        self.check_indices()
+        return out
+
     # -- sign rule of g / g_inv (overridden by the FlipSign subclasses, noisemapper.pyx:775-816) ------
     def _g_signs(self):
         return None
@@ -143,7 +158,7 @@ class NoiseMapper:
 
     def demap_noise(self, n_hat, symb):
         """noisemapper.pyx:391-404"""
-        return to_np(self.demap_noise_batch(to_dev(n_hat, torch.float64).reshape(-1),
+        return self._np_checked(self.demap_noise_batch(to_dev(n_hat, torch.float64).reshape(-1),
                                             to_dev(symb, torch.int64).reshape(-1)))
 
     def g_inv(self, n_hat, i):
@@ -168,7 +183,7 @@ class NoiseMapper:
 
     def demap_lappr_simplified_array(self, n, j):
         """noisemapper.pyx:605-621"""
-        return to_np(self._variant_batch(1, to_dev(n, torch.float64).reshape(-1), to_dev(j, torch.int64).reshape(-1)))
+        return self._np_checked(self._variant_batch(1, to_dev(n, torch.float64).reshape(-1), to_dev(j, torch.int64).reshape(-1)))
 
     def demap_lappr_simplified(self, n, j):
         """noisemapper.pyx:563-601"""
@@ -176,7 +191,7 @@ class NoiseMapper:
 
     def demap_lappr_sofisticated_array(self, n, j):
         """noisemapper.pyx:751-766"""
-        return to_np(self._variant_batch(2, to_dev(n, torch.float64).reshape(-1), to_dev(j, torch.int64).reshape(-1)))
+        return self._np_checked(self._variant_batch(2, to_dev(n, torch.float64).reshape(-1), to_dev(j, torch.int64).reshape(-1)))
 
     def demap_lappr_sofisticated(self, n, j):
         """noisemapper.pyx:624-748"""
@@ -258,7 +273,7 @@ class NoiseMapper:
         y = to_dev(y_samples, torch.float64).reshape(-1); idx = to_dev(index, torch.int64).reshape(-1)
         if y.numel() != idx.numel():
             raise ValueError("Input vectors sizes do not match")
-        return to_np(self.map_noise_batch(y, idx))
+        return self._np_checked(self.map_noise_batch(y, idx))
 
     def g(self, y, i):
         """noisemapper.pyx:289-292"""
@@ -268,7 +283,7 @@ class NoiseMapper:
         """noisemapper.pyx:310-345 (the kernels implement the default 1e-9 accuracy)."""
         if y_accuracy != 1e-9:
             raise ValueError("only y_accuracy=1e-9 is implemented on the device")
-        return float(to_np(self.g_inv_search_batch(np.array([float(n_hat)]), np.array([int(i)], dtype=np.int64)))[0])
+        return float(self._np_checked(self.g_inv_search_batch(np.array([float(n_hat)]), np.array([int(i)], dtype=np.int64)))[0])
 
     def demap_noise_search(self, n_hat, symb, y_accuracy=1e-9):
         """noisemapper.pyx:407-419"""
@@ -277,22 +292,22 @@ class NoiseMapper:
         nn = to_dev(n_hat, torch.float64).reshape(-1); ss = to_dev(symb, torch.int64).reshape(-1)
         if nn.numel() != ss.numel():
             raise ValueError("Sizes do not match")
-        return to_np(self.g_inv_search_batch(nn, ss))
+        return self._np_checked(self.g_inv_search_batch(nn, ss))
 
     def bare_llr(self, symb):
         """noisemapper.pyx:423-432"""
-        return to_np(self.bare_llr_batch(to_dev(symb, torch.int64).reshape(-1)))
+        return self._np_checked(self.bare_llr_batch(to_dev(symb, torch.int64).reshape(-1)))
 
     def demap_lappr(self, n, j):
         """noisemapper.pyx:450-540 for one (n, j) pair"""
-        return to_np(self.demap_lappr_array_batch(np.array([float(n)]), np.array([int(j)], dtype=np.int64)))
+        return self._np_checked(self.demap_lappr_array_batch(np.array([float(n)]), np.array([int(j)], dtype=np.int64)))
 
     def demap_lappr_array(self, n, j):
         """noisemapper.pyx:544-559"""
         nn = to_dev(n, torch.float64).reshape(-1); jj = to_dev(j, torch.int64).reshape(-1)
         if nn.numel() != jj.numel():
             raise ValueError("Sizes of transformed noise vector and tx symbols do not match")
-        return to_np(self.demap_lappr_array_batch(nn, jj))
+        return self._np_checked(self.demap_lappr_array_batch(nn, jj))
 
 
 class NoiseDemapper(NoiseMapper):

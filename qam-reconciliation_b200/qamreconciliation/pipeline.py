@@ -32,8 +32,10 @@ class Reconciler:
 
         Default: ONE call into the library (qr_reconcile_device), intermediates in library-owned scratch.
         stagewise=True runs the stages one library call at a time (same results; also returns the LLRs)."""
+        y = to_dev(y, torch.float64); x = to_dev(x, torch.int64)
+        if y.dim() != 2 or y.shape[1] != self.S or x.shape != y.shape:
+            raise ValueError(f"y and x must both have shape [frames, {self.S}], got {tuple(y.shape)} and {tuple(x.shape)}")
         if not stagewise:
-            y = to_dev(y, torch.float64); x = to_dev(x, torch.int64)
             B = y.shape[0]
             dev = y.device
             ok = torch.empty(B, dtype=torch.uint8, device=dev); it = torch.empty(B, dtype=torch.int32, device=dev)
@@ -75,9 +77,25 @@ class Reconciler:
         y: float64 [B, S], x: int64 [B, S] CPU tensors (pinned for asynchronous copies); `out` is a dict of
         preallocated CPU tensors: success uint8[B], iters int32[B], bit_errors int32[B], optional post [B, N]
         and word uint8[B, N]."""
+        for name, t, dt in (("y", y, torch.float64), ("x", x, torch.int64)):
+            if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != dt or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous CPU tensor of dtype {dt}")
+        if y.dim() != 2 or y.shape[1] != self.S or x.shape != y.shape:
+            raise ValueError(f"y and x must both have shape [frames, {self.S}], got {tuple(y.shape)} and {tuple(x.shape)}")
         B = y.shape[0]
         post = out.get("post")
         word = out.get("word")
+        for name, dt, shape in (("success", torch.uint8, (B,)), ("iters", torch.int32, (B,)),
+                                ("bit_errors", torch.int32, (B,))):
+            t = out.get(name)
+            if t is None or t.is_cuda or t.dtype != dt or tuple(t.shape) != shape or not t.is_contiguous():
+                raise ValueError(f"out[{name!r}] must be a contiguous CPU tensor of dtype {dt} and shape {shape}")
+        if post is not None and (post.is_cuda or tuple(post.shape) != (B, self.N) or not post.is_contiguous()
+                                 or post.dtype not in (torch.float32, torch.float64)):
+            raise ValueError(f"out['post'] must be a contiguous float CPU tensor of shape {(B, self.N)}")
+        if word is not None and (word.is_cuda or tuple(word.shape) != (B, self.N) or word.dtype != torch.uint8
+                                 or not word.is_contiguous()):
+            raise ValueError(f"out['word'] must be a contiguous uint8 CPU tensor of shape {(B, self.N)}")
         h = self.dec._handle(self.prec_code, self.lanes, self.schedule)
         _abi.check(_abi.lib().qr_reconcile_host(
             h, self.nm._h, self.mode, self.demap_code, self.alpha, y.data_ptr(), x.data_ptr(), B,
@@ -85,4 +103,5 @@ class Reconciler:
             post.data_ptr() if post is not None else None,
             (_abi.QR_F64 if post.dtype == torch.float64 else _abi.QR_F32) if post is not None else _abi.QR_F32,
             word.data_ptr() if word is not None else None, out["bit_errors"].data_ptr(), stream()))
+        self.nm.check_indices()      # (the call above has synchronised: this costs one 4-byte copy)
         return out

@@ -53,6 +53,15 @@ def test_graph_builds_on_host_without_a_device():
     assert b"degree" in L.qr_last_error()
     with pytest.raises(ValueError):
         _abi.check(_abi.QR_ERR_GRAPH)
+    # Matrix semantics (matrix.pyx:21-38): any edge list builds; the decoder refuses such a graph
+    assert L.qr_graph_create_any(bad_v.ctypes.data, bad_c.ctypes.data, 3, -1, C.byref(h)) == 0
+    assert L.qr_graph_info(h, C.byref(n), C.byref(c), C.byref(e), C.byref(mc), C.byref(mv)) == 0
+    assert (n.value, c.value, e.value, mc.value) == (3, 2, 3, 2)
+    elig = C.c_int(7)
+    assert L.qr_graph_fused_eligible(h, C.byref(elig)) == 0 and elig.value == 0
+    d = C.c_void_p()
+    assert L.qr_decoder_create(h, _abi.QR_F64, 32, C.byref(d)) != 0      # (no device, and not decodable)
+    L.qr_graph_destroy(h)
 
 
 def test_compute_classes_fail_loudly_without_cuda():

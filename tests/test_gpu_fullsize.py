@@ -1,0 +1,167 @@
+"""Oracle parity AT THE SIZES THE BENCH RUNS (BASELINE configs 2, 3 and 4, full size).
+
+The CUDA path is compared frame by frame with the CPU oracle (oracle/port.py -> oracle/qr_oracle.c, pinned to the
+compiled reference by tests/test_oracle_golden.py), reference: Decoder._decode, decoder.pyx:391-436.
+
+  * the front of the chain (hard decision, Gray bits, syndrome) bit for bit, the softening metric to 1e-14,
+    Alice's LLRs (exact replay) to 1e-9;
+  * the fp64 decoder, fed the ORACLE's LLRs and syndromes so that both sides start from identical bits, through
+    every schedule the graph admits (two-phase persistent 0, fused 2): success flags and iteration counts
+    exact, posteriors to 1e-9 relative;
+  * the fp32 fast mode on the same inputs: same success flags, same hard decisions on the converged frames.
+
+Tolerances: 1e-9 relative + 1e-9 absolute on posteriors (CUDA exp/log differ from glibc in the last ulp; a frame
+that runs to the iteration limit WITHOUT converging amplifies that ulp chaotically, so for such frames the bar is
+the one a user can observe: >= 99.9 % equal hard decisions and posteriors within 1e-6 on the bits that agree).
+"""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import qamreconciliation as qr
+    from qamreconciliation import codes
+    from oracle import port as orc
+    return qr, codes, orc
+
+
+def oracle_chain(orc, vid, cid, bps, cfg, n0, x, y, maxiter):
+    """The reference's loop body (sims/reconciliation.pyx:129-153) per frame on the CPU oracle; frames run on a
+    thread pool (the ctypes calls release the GIL)."""
+    pa = orc.PAMAlphabet(bps, 2.0); nm = orc.NoiseMapper(pa, n0, cfg)
+    mat = orc.Matrix(vid, cid)
+
+    def one(f):
+        dec = orc.Decoder(vid, cid)          # one handle per thread: the oracle decoder owns its scratch
+        xh = nm.hard_decide_index(y[f]); word = pa.demap_symbols_to_bits(xh)
+        nh = nm.map_noise(y[f], xh)
+        llr = nm.demap_lappr_array(nh, x[f])
+        synd = mat.eval_syndrome(word)
+        ok, it, post = dec.decode(llr, synd, maxiter)
+        return dict(xh=xh, word=word, nh=nh, llr=llr, synd=synd, ok=int(ok), it=int(it), post=post)
+
+    with ThreadPoolExecutor(max_workers=min(len(x), os.cpu_count() or 1)) as pool:
+        return list(pool.map(one, range(len(x))))
+
+
+def compare_decoder(qr, dec, want, maxiter, schedules, lanes):
+    llr = torch.tensor(np.stack([w["llr"] for w in want]), device="cuda")
+    synd = torch.tensor(np.stack([w["synd"] for w in want]), device="cuda")
+    w_ok = np.array([w["ok"] for w in want]); w_it = np.array([w["it"] for w in want])
+    w_post = np.stack([w["post"] for w in want])
+    for sched in schedules:
+        ok, it, post = dec.decode_batch(llr, synd, maxiter, precision="fp64", schedule=sched, lanes=lanes)
+        ok, it, post = ok.cpu().numpy(), it.cpu().numpy(), post.cpu().numpy()
+        assert np.array_equal(ok, w_ok), (sched, ok, w_ok)
+        assert np.array_equal(it, w_it), (sched, it, w_it)
+        for f in range(len(want)):
+            if w_ok[f]:
+                np.testing.assert_allclose(post[f], w_post[f], rtol=1e-9, atol=1e-9, err_msg=f"schedule {sched} frame {f}")
+            else:
+                same = (post[f] < 0) == (w_post[f] < 0)
+                assert same.mean() >= 0.999, (sched, f, same.mean())
+                np.testing.assert_allclose(post[f][same], w_post[f][same], rtol=1e-6, atol=1e-6)
+    # fp32 fast mode on the same inputs
+    for sched in schedules:
+        ok32, it32, post32 = dec.decode_batch(llr.float(), synd, maxiter, precision="fp32", schedule=sched, lanes=lanes)
+        ok32, it32, post32 = ok32.cpu().numpy(), it32.cpu().numpy(), post32.cpu().numpy()
+        assert np.array_equal(ok32, w_ok), (sched, ok32, w_ok)
+        conv = w_ok == 1
+        if conv.any():
+            assert np.abs(it32[conv] - w_it[conv]).max() <= 2, (sched, it32, w_it)
+            assert np.array_equal(post32[conv] < 0, w_post[conv] < 0), sched
+    return w_ok, w_it
+
+
+def compare_front(qr, nm, mat, want, x, y, exact_llr=True):
+    idx, nh, word = nm.front_end_batch(torch.tensor(y, device="cuda"))
+    assert np.array_equal(idx.cpu().numpy(), np.stack([w["xh"] for w in want]))
+    assert np.array_equal(word.cpu().numpy(), np.stack([w["word"] for w in want]))
+    np.testing.assert_allclose(nh.cpu().numpy(), np.stack([w["nh"] for w in want]), rtol=0, atol=1e-14)
+    synd = mat.eval_syndrome_batch(word)
+    assert np.array_equal(synd.cpu().numpy(), np.stack([w["synd"] for w in want]))
+    if exact_llr:
+        llr = nm.demap_lappr_array_batch(nh, torch.tensor(x, device="cuda"), mode="exact")
+        np.testing.assert_allclose(llr.cpu().numpy(), np.stack([w["llr"] for w in want]), rtol=1e-9, atol=1e-9)
+    llr_f = nm.demap_lappr_array_batch(nh, torch.tensor(x, device="cuda"), mode="fast")
+    np.testing.assert_allclose(llr_f.cpu().numpy(), np.stack([w["llr"] for w in want]), rtol=1e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize("snr", [3.0, 4.0, 4.6])
+def test_config2_full_size_against_oracle(env, snr):
+    """BASELINE config 2: (3,6)-regular n = 64800, 4-PAM Alternating, maxiter 50 -- the code, seed and operating
+    points bench.py runs (3 dB: no frame converges; 4 dB: waterfall; 4.6 dB: every frame converges)."""
+    qr, codes, orc = env
+    n, bps, frames = 64800, 2, 8
+    vid, cid = codes.regular_ldpc(n, 3, 6, seed=1)
+    cfg = np.array([0, 1, 0, 1], dtype=np.uint8)
+    pa = qr.PAMAlphabet(bps, 2)
+    n0 = pa.variance * 10 ** (-snr / 10) / 2
+    rng = np.random.default_rng(int(snr * 10))
+    x = rng.integers(0, 4, size=(frames, n // bps)).astype(np.int64)
+    y = pa.constellation[x] + np.sqrt(n0) * rng.normal(size=x.shape)
+    want = oracle_chain(orc, vid, cid, bps, cfg, n0, x, y, 50)
+    nm = qr.NoiseMapper(pa, n0, cfg); mat = qr.Matrix(vid, cid); dec = qr.Decoder(vid, cid)
+    compare_front(qr, nm, mat, want, x, y)
+    w_ok, w_it = compare_decoder(qr, dec, want, 50, schedules=(0, 2), lanes=32)
+    if snr == 3.0:
+        assert not w_ok.any() and (w_it == 50).all()
+    if snr == 4.6:
+        assert w_ok.all() and w_it.max() < 30
+
+
+def test_config3_full_size_against_oracle(env):
+    """BASELINE config 3: irregular R = 0.2, n = 131070 (= 3 * 43690), 8-PAM, maxiter 100; one operating point
+    where frames converge and one where they do not."""
+    qr, codes, orc = env
+    n, c, bps = 131070, 104856, 3
+    vid, cid = codes.irregular_ldpc(n, c, [3, 8], [0.9, 0.1], seed=3)
+    cfg = np.zeros(8, dtype=np.uint8); cfg[1::2] = 1
+    pa = qr.PAMAlphabet(bps, 2)
+    dec = qr.Decoder(vid, cid); mat = qr.Matrix(vid, cid)
+    scheds = (0, 2) if dec.fused_eligible else (0,)
+    seen = []
+    for snr in (3.0, 9.0):
+        n0 = pa.variance * 10 ** (-snr / 10) / 2
+        rng = np.random.default_rng(31 + int(snr))
+        x = rng.integers(0, 8, size=(2, n // bps)).astype(np.int64)
+        y = pa.constellation[x] + np.sqrt(n0) * rng.normal(size=x.shape)
+        want = oracle_chain(orc, vid, cid, bps, cfg, n0, x, y, 100)
+        nm = qr.NoiseMapper(pa, n0, cfg)
+        compare_front(qr, nm, mat, want, x, y)
+        w_ok, _ = compare_decoder(qr, dec, want, 100, schedules=scheds, lanes=32)
+        seen += list(w_ok)
+    assert 0 in seen and 1 in seen, seen
+
+
+def test_config4_full_size_against_oracle(env):
+    """BASELINE config 4: QKD-scale irregular R = 0.1, n = 2^20, bps = 1, maxiter 60."""
+    qr, codes, orc = env
+    n, c, bps = 1 << 20, 943718, 1
+    vid, cid = codes.irregular_ldpc(n, c, [3, 4, 10], [0.8, 0.15, 0.05], seed=4)
+    cfg = np.array([0, 1], dtype=np.uint8)
+    pa = qr.PAMAlphabet(bps, 2)
+    dec = qr.Decoder(vid, cid); mat = qr.Matrix(vid, cid)
+    scheds = (0, 2) if dec.fused_eligible else (0,)
+    seen = []
+    for snr in (-12.0, -3.0):
+        n0 = pa.variance * 10 ** (-snr / 10) / 2
+        rng = np.random.default_rng(41 + int(-snr))
+        x = rng.integers(0, 2, size=(1, n // bps)).astype(np.int64)
+        y = pa.constellation[x] + np.sqrt(n0) * rng.normal(size=x.shape)
+        want = oracle_chain(orc, vid, cid, bps, cfg, n0, x, y, 60)
+        nm = qr.NoiseMapper(pa, n0, cfg)
+        compare_front(qr, nm, mat, want, x, y, exact_llr=(snr > -5))
+        w_ok, _ = compare_decoder(qr, dec, want, 60, schedules=scheds, lanes=32)
+        seen += list(w_ok)
+    assert 0 in seen and 1 in seen, seen

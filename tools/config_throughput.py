@@ -33,32 +33,44 @@ def run(name, vid, cid, bps, snr, cfg, frames, maxiter, lanes):
     synd = mat.eval_syndrome_batch(word)
     llr = nm.demap_lappr_array_batch(nh, x, mode="fast", out_dtype=torch.float32)
     del y, nh
-    ts = []
-    for rep in range(3):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ok, it, post = dec.decode_batch(llr, synd, maxiter, precision="fp32", lanes=lanes, schedule=3)
-        e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    fi, steps = dec.last_stats("fp32", lanes)
-    ms = min(ts[1:])
-    bpi = 4 * E * 4 + 2 * n * 4 + c
-    print(json.dumps({"config": name, "n": n, "checks": c, "edges": int(E), "frames": frames, "lanes": lanes,
-                      "max_iterations": maxiter, "avg_iterations": fi / frames, "converged": int(ok.sum()),
-                      "decode_ms": ms, "frames_per_s": frames / ms * 1e3, "edge_updates_per_s": fi * E / ms * 1e3,
-                      "algorithmic_GBps": fi * bpi / ms / 1e6}))
+    for lanes in (lanes if isinstance(lanes, (list, tuple)) else [lanes]):
+        ts = []
+        for rep in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ok, it, post = dec.decode_batch(llr, synd, maxiter, precision="fp32", lanes=lanes, schedule=SCHEDULE)
+            e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        fi, steps = dec.last_stats("fp32", lanes)
+        ms = min(ts[1:])
+        bpi = 4 * E * 4 + 2 * n * 4 + c
+        print(json.dumps({"config": name, "n": n, "checks": c, "edges": int(E), "frames": frames, "lanes": lanes,
+                          "max_iterations": maxiter, "avg_iterations": fi / frames, "converged": int(ok.sum()),
+                          "decode_ms": ms, "frames_per_s": frames / ms * 1e3, "edge_updates_per_s": fi * E / ms * 1e3,
+                          "algorithmic_GBps": fi * bpi / ms / 1e6}), flush=True)
+        from qamreconciliation import _abi
+        for key in list(dec._dec):      # free this lane count's workspace before the next one
+            _abi.lib().qr_decoder_destroy(dec._dec.pop(key))
+
+
+SCHEDULE = 3
 
 
 def main():
+    global SCHEDULE
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames3", type=int, default=512)
     ap.add_argument("--frames4", type=int, default=256)
+    ap.add_argument("--lanes3", default="256", help="comma list of resident-frame counts tried for config 3")
+    ap.add_argument("--lanes4", default="128", help="the same for config 4")
+    ap.add_argument("--schedule", type=int, default=3)
     a = ap.parse_args()
+    SCHEDULE = a.schedule
     vid, cid = codes.irregular_ldpc(131070, 104856, [3, 8], [0.9, 0.1], seed=3)
     cfg = np.zeros(8, dtype=np.uint8); cfg[1::2] = 1
-    run("3: irregular n=131070 R=0.2 8-PAM", vid, cid, 3, 3.0, cfg, a.frames3, 100, 256)
+    run("3: irregular n=131070 R=0.2 8-PAM", vid, cid, 3, 3.0, cfg, a.frames3, 100, [int(v) for v in a.lanes3.split(",")])
     vid, cid = codes.irregular_ldpc(1 << 20, 943718, [3, 4, 10], [0.8, 0.15, 0.05], seed=4)
-    run("4: irregular n=2^20 R=0.1 2-PAM", vid, cid, 1, -12.0, np.array([0, 1], dtype=np.uint8), a.frames4, 60, 128)
+    run("4: irregular n=2^20 R=0.1 2-PAM", vid, cid, 1, -12.0, np.array([0, 1], dtype=np.uint8), a.frames4, 60, [int(v) for v in a.lanes4.split(",")])
 
 
 if __name__ == "__main__":
