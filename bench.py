@@ -14,7 +14,10 @@ below the waterfall so that every frame runs all 50 iterations (the worst case a
 Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same
 metric through the host-buffer C-ABI call (qr_reconcile_host) with the copies inside the timed
 region; `roofline` = the decoder kernel against the measured HBM peak; `cpu_baseline` = the CPU
-oracle port timed on this box's cores on a bounded sample of the same frames.
+oracle port timed on this box's cores on frames taken from the GPU batch, with its agreement with the
+GPU's fp64 mode on those frames.  At N = 1 the line also carries `operating_points`: the same measurement
+in the waterfall (4 dB) and above it (5 dB), the fp64 parity mode, and the decoder on BASELINE configs 3 and
+4 (`--no-extras` skips them).
 """
 import argparse
 import json
@@ -57,6 +60,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames per CPU worker (0 = auto)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the supplementary operating points (4 dB, 5 dB, fp64, configs 3 and 4)")
     a = ap.parse_args()
     if a.schedule < 0:
         a.schedule = 2
@@ -161,21 +166,25 @@ def _cpu_init(kind, n, snr):
     cfg = np.zeros(1 << BPS, dtype=np.uint8); cfg[1::2] = 1
     n0 = pa.variance * 10 ** (-snr / 10) / 2
     _W.update(kind=kind, n=n, n0=n0, cfg=cfg, pa=pa, dec=dec, mat=mat, nm=NM(pa, n0, cfg),
-              a=np.asarray(pa.constellation), setup=time.time() - t_setup, onm=None)
+              a=np.asarray(pa.constellation), setup=time.time() - t_setup)
 
 
 def _cpu_step(args):
-    """One frame at a time through the whole chain (the north star's CPU protocol)."""
-    seeds, demap_div = args
+    """One WHOLE frame at a time through the whole chain (the north star's CPU protocol): every stage on every
+    symbol, nothing scaled.  args = list of (seed | (y, x)) frames: a seed draws the frame here, a (y, x) pair is a
+    frame copied out of the GPU batch."""
     W = _W
     n, n0, pa, nm, dec, mat, a = W["n"], W["n0"], W["pa"], W["nm"], W["dec"], W["mat"], W["a"]
     S = n // BPS
     t_chain = t_demap = t_dec = 0.0
-    iters = 0
-    for seed in seeds:
-        rng = np.random.default_rng(seed)
-        x = rng.integers(0, 1 << BPS, size=S).astype(np.int64)
-        y = a[x] + np.sqrt(n0) * rng.normal(size=S)
+    res = []
+    for fr in args:
+        if isinstance(fr, tuple):
+            y, x = np.array(fr[0], dtype=np.float64), np.array(fr[1], dtype=np.int64)
+        else:
+            rng = np.random.default_rng(fr)
+            x = rng.integers(0, 1 << BPS, size=S).astype(np.int64)
+            y = a[x] + np.sqrt(n0) * rng.normal(size=S)
         t0 = time.time()
         xh = np.array(nm.hard_decide_index(y.copy()), dtype=np.int64)
         nh = np.array(nm.map_noise(y.copy(), xh.copy()))
@@ -184,23 +193,14 @@ def _cpu_step(args):
             word = word.view(np.uint8)
         synd = np.array(mat.eval_syndrome(word.copy()), dtype=np.uint8)
         t1 = time.time()
-        sub = S // demap_div
-        lap_part = np.array(nm.demap_lappr_array(nh[:sub].copy(), x[:sub].copy()))
+        lap = np.array(nm.demap_lappr_array(nh.copy(), x.copy()))
         t2 = time.time()
-        if demap_div > 1:
-            # the decoder needs LLRs for the whole frame: the oracle port supplies the rest (untimed)
-            if W["onm"] is None:
-                from oracle import port as orc2
-                W["onm"] = orc2.NoiseMapper(orc2.PAMAlphabet(BPS, 2), n0, W["cfg"])
-            lap = np.concatenate([lap_part, W["onm"].demap_lappr_array(nh[sub:], x[sub:])])
-        else:
-            lap = lap_part
-        t3 = time.time()
         ok, it, post = dec.decode(lap.copy(), synd.copy(), MAXITER)
-        t4 = time.time()
-        t_chain += t1 - t0; t_demap += (t2 - t1) * demap_div; t_dec += t4 - t3
-        iters += int(it)
-    return dict(setup=W["setup"], chain=t_chain, demap=t_demap, dec=t_dec, frames=len(seeds), iters=iters)
+        t3 = time.time()
+        t_chain += t1 - t0; t_demap += t2 - t1; t_dec += t3 - t2
+        res.append((int(ok), int(it), np.array(post, dtype=np.float64) if isinstance(fr, tuple) else None))
+    return dict(setup=W["setup"], chain=t_chain, demap=t_demap, dec=t_dec, frames=len(args),
+                iters=sum(r[1] for r in res), results=res)
 
 
 class CpuArm:
@@ -211,69 +211,223 @@ class CpuArm:
         self.P = workers or os.cpu_count() or 1
         self.pool = mp.get_context("spawn").Pool(self.P, initializer=_cpu_init, initargs=(kind, n, snr))
         self.step_no = 0
+        self.pool.map(_noop, range(self.P), chunksize=1)      # constructors done before anything is timed
 
-    def step(self, frames_per_worker, demap_div):
-        jobs = [([100000 * self.step_no + 1000 * w + f for f in range(frames_per_worker)], demap_div)
-                for w in range(self.P)]
+    def step(self, frames_per_worker=1, given=None):
+        """One step: every worker takes `frames_per_worker` frames, one frame per call; the wall time of the step is
+        measured here, around the whole map.  given: list (per worker) of lists of (y, x) frames."""
+        if given is not None:
+            jobs = given
+        else:
+            jobs = [[100000 * self.step_no + 1000 * w + f for f in range(frames_per_worker)] for w in range(self.P)]
         self.step_no += 1
         t0 = time.time()
         res = self.pool.map(_cpu_step, jobs, chunksize=1)
         wall = time.time() - t0
-        per_frame = [(r["chain"] + r["demap"] + r["dec"]) / r["frames"] for r in res]
-        # every worker runs concurrently on its own core: aggregate rate = sum of per-worker rates
-        return dict(fps=sum(1.0 / t for t in per_frame), cores=self.P, wall=wall,
+        frames = sum(r["frames"] for r in res)
+        return dict(fps=frames / wall, frames=frames, cores=self.P, wall=wall,
                     setup=max(r["setup"] for r in res),
                     chain=float(np.mean([r["chain"] / r["frames"] for r in res])),
                     demap=float(np.mean([r["demap"] / r["frames"] for r in res])),
                     dec=float(np.mean([r["dec"] / r["frames"] for r in res])),
-                    iters=float(np.mean([r["iters"] / r["frames"] for r in res])))
+                    iters=float(np.mean([r["iters"] / r["frames"] for r in res])),
+                    results=[r["results"] for r in res])
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
 
-def run_cpu(kind, n, snr, frames_per_worker, demap_div, workers=None):
-    arm = CpuArm(kind, n, snr, workers)
-    try:
-        return arm.step(frames_per_worker, demap_div)
-    finally:
-        arm.close()
+def _noop(_):
+    time.sleep(0.05)
+    return 0
+
+
+def workload_config(a, n_sets=2):
+    """The `config` object of the JSON line: the workload both arms are quoted on."""
+    B, S = a.frames, a.n // BPS
+    return {"workload": workload_name(a.n, a.snr), "frames_per_gpu_per_step": B, "demap": a.demap,
+            "decoder_lanes": a.lanes or 512, "schedule": {0: "persistent", 1: "launch", 2: "fused", 3: "auto"}[a.schedule],
+            "l2_policy": f"{n_sets} alternating input sets of {B * S * 16 / 1e9:.1f} GB each (>> 126 MB L2)"}
 
 
 def reference_arm(a):
-    """The reference's own CPU implementation of the path on this box's cores."""
+    """The reference's own CPU implementation of the path on this box's cores: the UNMODIFIED compiled reference
+    (oracle/_ref) where it was built, else the oracle port.  One step = every host core decodes ONE whole frame of the
+    workload (all stages on all symbols, nothing scaled or modelled); `ms_per_step` is the measured wall time of a
+    step and `value` = frames of the step / that wall time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import build_ref
     kind = "reference" if build_ref.have_ref() else "port"
-    # The reference's demap_lappr_array costs ~27 s per n=64800 frame (Python-level scipy.erf per call):
-    # it is timed on the first 1/16 of each frame's symbols and scaled by 16, everything else on whole frames.
-    div = 16 if kind == "reference" else 1
     arm = CpuArm(kind, a.n, a.snr)
-    results = [arm.step(1, div) for _ in range(a.warmup + a.steps)]
+    results = [arm.step(1) for _ in range(a.warmup + a.steps)]
     arm.close()
     res = results[a.warmup:] or results
-    fps = float(np.mean([r["fps"] for r in res]))
-    ms = float(np.mean([1000.0 * r["cores"] / r["fps"] for r in res]))
+    wall = float(np.sum([r["wall"] for r in res]))
+    frames = int(np.sum([r["frames"] for r in res]))
+    fps = frames / wall
+    ms = 1000.0 * wall / len(res)
     K = a.n // 2
-    sample = (f"per step: {res[0]['cores']} worker processes x 1 frame each, one frame per process; "
-              f"hard decision/map_noise/bits/syndrome/decode on the whole frame, demap_lappr_array on "
-              f"1/{div} of the symbols scaled x{div}; decoder constructor ({res[0]['setup']:.0f} s) excluded; "
-              f"per frame: chain {res[0]['chain']:.3f} s, demap {res[0]['demap']:.2f} s, decode {res[0]['dec']:.2f} s")
+    r0 = res[0]
+    sample = (f"per step: {r0['cores']} worker processes x 1 whole frame each (one frame per process and call), every "
+              f"stage on all {a.n // BPS} symbols; wall time of the step measured around the pool; decoder constructor "
+              f"({r0['setup']:.0f} s per process) outside the steps; per frame: hard decision + map_noise + bits + syndrome "
+              f"{r0['chain']:.3f} s, demap_lappr_array {r0['demap']:.2f} s, decode {r0['dec']:.2f} s "
+              f"({r0['iters']:.0f} iterations)")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a.n, a.snr), "frames_per_step": res[0]["cores"]},
+            "config": workload_config(a),
+            "frames_per_step": r0["frames"],
             "info_gbit_per_s": fps * K / 1e9,
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": res[0]["cores"], "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": r0["cores"], "kind": kind, "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------- our arm
+class Workload:
+    """Code, decoder, mapper and synthetic inputs of one operating point on this rank's GPU."""
+
+    def __init__(self, torch, qr, codes, dev, rank, vid, cid, bps, snr, cfg, frames, maxiter, precision, demap, lanes,
+                 schedule, n_sets=2, dec=None):
+        from qamreconciliation.pipeline import Reconciler
+        self.torch, self.dev = torch, dev
+        self.n, self.C, self.E = int(vid.max()) + 1, int(cid.max()) + 1, int(vid.size)
+        self.K, self.S, self.bps = self.n - self.C, self.n // bps, bps
+        self.B, self.maxiter, self.precision, self.lanes, self.schedule = frames, maxiter, precision, lanes, schedule
+        self.dec = dec if dec is not None else qr.Decoder(vid, cid)
+        self.pa = qr.PAMAlphabet(bps, 2)
+        self.n0 = self.pa.variance * 10 ** (-snr / 10) / 2
+        self.nm = qr.NoiseMapper(self.pa, self.n0, cfg)
+        self.rec = Reconciler(self.dec, self.nm, precision=precision, demap=demap, lanes=lanes or None, schedule=schedule)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + rank)
+        const = torch.tensor(self.pa.constellation, device=dev)
+        # distinct inputs per step (config 2: 4096 x 32400 x 16 B = 2.1 GB per set, >> L2)
+        self.n_sets = n_sets
+        self.xs = [torch.randint(0, self.pa.order, (frames, self.S), device=dev, generator=gen) for _ in range(n_sets)]
+        self.ys = [const[x] + float(np.sqrt(self.n0)) * torch.randn((frames, self.S), device=dev, dtype=torch.float64,
+                                                                    generator=gen) for x in self.xs]
+        self.w = 4 if precision == "fp32" else 8
+        self.bytes_per_frame_iter = 4 * self.E * self.w + 2 * self.n * self.w + self.C
+
+    def step(self, i):
+        return self.rec.run_device(self.ys[i % self.n_sets], self.xs[i % self.n_sets], self.maxiter, k_info=self.K)
+
+    def device_leg(self, steps, warmup, barrier, all_reduce=None, sampler=None):
+        """W untimed + K timed steps with the inputs resident in HBM; the counters (and, on N > 1, their all-reduce:
+        the path's only exchange) are inside the timed region.  Returns (elapsed ms on this rank, counters)."""
+        torch = self.torch
+        for i in range(warmup):
+            self.step(i)
+        barrier()
+        if sampler is not None:
+            sampler.skip = len(sampler.samples)       # samples taken before the timed region do not count
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        counters = torch.zeros(5, dtype=torch.int64, device=self.dev)
+        b_frames = torch.tensor(self.B, dtype=torch.int64, device=self.dev)
+        barrier()
+        ev[0].record()
+        for i in range(steps):
+            out = self.step(warmup + i)
+            # (b_frames lives on the device: building it here would be a synchronous host-to-device copy every
+            # step, which stalls the launch queue behind the whole step)
+            counters += torch.stack([out["bit_errors"].sum(dtype=torch.int64), (out["bit_errors"] > 0).sum(),
+                                     out["success"].sum(dtype=torch.int64),
+                                     (out["iters"].to(torch.int64) * out["success"].to(torch.int64)).sum(),
+                                     b_frames])
+        if all_reduce is not None:
+            all_reduce(counters)                      # BER / FER / iteration counters: one tiny NCCL all-reduce
+        ev[1].record()
+        barrier()
+        return ev[0].elapsed_time(ev[1]), counters
+
+    def decoder_leg(self, reps):
+        """The decoder kernel alone on the LLRs / syndromes of input set 0: CUDA events around the launch (torch's
+        current stream is the stream the library launches on).  Returns (mean ms, frame-iterations, steps)."""
+        torch = self.torch
+        out_s = self.rec.run_device(self.ys[0], self.xs[0], self.maxiter, k_info=self.K, stagewise=True)
+        llr, synd = out_s["llr"], out_s["synd"]
+        del out_s
+        kw = dict(precision=self.precision, lanes=self.lanes or None, schedule=self.schedule)
+        for _ in range(2):
+            self.dec.decode_batch(llr, synd, self.maxiter, **kw)
+        torch.cuda.synchronize()
+        kt = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.dec.decode_batch(llr, synd, self.maxiter, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            kt.append(e0.elapsed_time(e1))
+        fi, steps_exec = self.dec.last_stats(self.precision, self.lanes or None)
+        return float(np.mean(kt)), fi, steps_exec
+
+    def e2e_leg(self, steps, warmup, barrier):
+        """Through qr_reconcile_host: pinned host y / x in, success, iterations, bit errors and final LLRs out, the
+        copies inside the timed region.  Returns (seconds on this rank, h2d bytes, d2h bytes per step)."""
+        torch = self.torch
+        hy = [y.cpu().pin_memory() for y in self.ys]
+        hx = [x.cpu().pin_memory() for x in self.xs]
+        outs = dict(success=torch.empty(self.B, dtype=torch.uint8).pin_memory(),
+                    iters=torch.empty(self.B, dtype=torch.int32).pin_memory(),
+                    bit_errors=torch.empty(self.B, dtype=torch.int32).pin_memory(),
+                    post=torch.empty((self.B, self.n), dtype=torch.float32 if self.precision == "fp32" else torch.float64).pin_memory())
+        for i in range(min(warmup, 2)):
+            self.rec.run_host(hy[i % self.n_sets], hx[i % self.n_sets], self.maxiter, self.K, outs)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            self.rec.run_host(hy[i % self.n_sets], hx[i % self.n_sets], self.maxiter, self.K, outs)
+        barrier()
+        el = time.perf_counter() - t0
+        h2d = self.B * self.S * 16
+        d2h = self.B * (1 + 4 + 4) + outs["post"].numel() * outs["post"].element_size()
+        return el, h2d, d2h
+
+    def roofline(self, k_ms, fi, kname, traffic=None):
+        peak, peak_src = peaks()
+        achieved = fi * self.bytes_per_frame_iter / (k_ms / 1e3) / 1e9
+        r = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+             "algorithmic_bytes_per_launch": fi * self.bytes_per_frame_iter, "launch_ms": k_ms,
+             "edge_updates_per_s": fi * self.E / (k_ms / 1e3), "frame_iterations_per_launch": fi,
+             "decode_only_frames_per_s": self.B / (k_ms / 1e3)}
+        if traffic:
+            # what the HBM really carried (ncu dram__bytes of the same launch) over the live launch time
+            r["dram_GBps"] = traffic / (k_ms / 1e3) / 1e9
+            r["dram_frac"] = r["dram_GBps"] / peak
+        return r
+
+
+def lookup_traffic(n, B, maxiter, precision, schedule, lanes, fi):
+    """DRAM bytes of the same launch from the committed ncu --set full captures (profiles/r*_traffic.json)."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json"))):
+        try:
+            tj = json.load(open(path))
+        except Exception:
+            continue
+        for ent in tj.get("entries", []):
+            c = ent["config"]
+            sched = {"persistent": 0, "launch": 1, "fused": 2}[c["schedule"]]
+            if (c["n"], c["frames"], c["max_iterations"], c["precision"], sched, c["lanes"]) == \
+                    (n, B, maxiter, precision, schedule, lanes) and fi == ent.get("frame_iterations", B * maxiter):
+                best = ent["dram_bytes_per_launch"]        # later rounds override earlier ones
+    return best
+
+
+KERNEL_NAMES = {0: "k_persistent (decoder, two-phase, one launch per batch)", 1: "k_check+k_var",
+                2: "k_fused (decoder, fused flooding iteration, one launch per batch)",
+                3: "decoder (schedule chosen by the library)"}
+
+
 def ours(a):
     import torch
     import torch.distributed as dist
@@ -290,39 +444,29 @@ def ours(a):
         dist.barrier()
     import qamreconciliation as qr
     from qamreconciliation import codes
-    from qamreconciliation.pipeline import Reconciler
 
+    dev = torch.device("cuda", local)
     n = a.n
     vid, cid = codes.regular_ldpc(n, DV, DC, seed=CODE_SEED)
-    E, C = vid.size, n * DV // DC
-    K = n - C
-    S = n // BPS
-    dec = qr.Decoder(vid, cid)
-    pa = qr.PAMAlphabet(BPS, 2)
-    cfg = np.zeros(pa.order, dtype=np.uint8); cfg[1::2] = 1
-    n0 = pa.variance * 10 ** (-a.snr / 10) / 2
-    nm = qr.NoiseMapper(pa, n0, cfg)
-    rec = Reconciler(dec, nm, precision=a.precision, demap=a.demap, lanes=a.lanes or None, schedule=a.schedule)
-    B = a.frames
-    dev = torch.device("cuda", local)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    const = torch.tensor(pa.constellation, device=dev)
-    # distinct inputs per step (working set >> L2: 4096 x 32400 x 16 B = 2.1 GB per step)
-    n_sets = 2
-    xs = [torch.randint(0, pa.order, (B, S), device=dev, generator=gen) for _ in range(n_sets)]
-    ys = [const[x] + float(np.sqrt(n0)) * torch.randn((B, S), device=dev, dtype=torch.float64, generator=gen)
-          for x in xs]
-    w = 4 if a.precision == "fp32" else 8
-    bytes_per_frame_iter = 4 * E * w + 2 * n * w + C
+    cfg = np.zeros(1 << BPS, dtype=np.uint8); cfg[1::2] = 1
+    wl = Workload(torch, qr, codes, dev, rank, vid, cid, BPS, a.snr, cfg, a.frames, MAXITER, a.precision, a.demap,
+                  a.lanes, a.schedule)
+    B, K, S = wl.B, wl.K, wl.S
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i):
-        return rec.run_device(ys[i % n_sets], xs[i % n_sets], MAXITER, k_info=K)
+    def all_reduce_sum(t):
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- device-resident leg
     # nvidia-smi is started BEFORE the warm-up: its start-up takes ~0.2 s, and a GPU left idle that long drops its
@@ -331,129 +475,148 @@ def ours(a):
     if rank == 0:
         sampler.start()
         sampler.wait_ready()
-    for i in range(a.warmup):
-        out = step(i)
-    barrier()
-    sampler.skip = len(sampler.samples)       # samples taken before the timed region do not count
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    dec_ev = []
-    counters = torch.zeros(5, dtype=torch.int64, device=dev)
-    b_frames = torch.tensor(B, dtype=torch.int64, device=dev)
-    barrier()
-    ev[0].record()
-    frame_iters = 0
-    for i in range(a.steps):
-        out = step(a.warmup + i)
-        # (b_frames lives on the device: building it here would be a synchronous host-to-device copy every step,
-        # which stalls the launch queue behind the whole step)
-        counters += torch.stack([out["bit_errors"].sum(dtype=torch.int64), (out["bit_errors"] > 0).sum(),
-                                 out["success"].sum(dtype=torch.int64),
-                                 (out["iters"].to(torch.int64) * out["success"].to(torch.int64)).sum(),
-                                 b_frames])
-    ev[1].record()
-    barrier()
-    elapsed_ms = ev[0].elapsed_time(ev[1])
+    elapsed_ms, counters = wl.device_leg(a.steps, a.warmup, barrier, all_reduce_sum, sampler)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM)     # the only data exchange of the path
-    elapsed_ms = float(t.item())
+    elapsed_ms = max_over_ranks(elapsed_ms)
     total_frames = B * a.steps * world
     value = total_frames / (elapsed_ms / 1e3)
 
-    # ---- decoder kernel alone (roofline): same inputs, events around the decode call only
-    out_s = rec.run_device(ys[0], xs[0], MAXITER, k_info=K, stagewise=True)
-    llr = out_s["llr"]; synd = out_s["synd"]
-    del out_s
-    for _ in range(2):
-        dec.decode_batch(llr, synd, MAXITER, precision=a.precision, lanes=a.lanes or None, schedule=a.schedule)
-    torch.cuda.synchronize()
-    kt = []
-    for _ in range(max(3, a.steps)):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ok_, it_, _ = dec.decode_batch(llr, synd, MAXITER, precision=a.precision, lanes=a.lanes or None,
-                                       schedule=a.schedule)
-        e1.record()
-        torch.cuda.synchronize()
-        kt.append(e0.elapsed_time(e1))
-    fi, steps_exec = dec.last_stats(a.precision, a.lanes or None)
-    k_ms = float(np.mean(kt))
-    peak, peak_src = peaks()
-    achieved = fi * bytes_per_frame_iter / (k_ms / 1e3) / 1e9
-    traffic = None
-    try:   # DRAM bytes of the same launch from the committed ncu --set full captures (profiles/)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        for ent in tj.get("entries", [tj]):
-            c = ent["config"]
-            sched = {"persistent": 0, "launch": 1, "fused": 2}[c["schedule"]]
-            if (c["n"], c["frames"], c["max_iterations"], c["precision"], sched, c["lanes"]) == \
-                    (n, B, MAXITER, a.precision, a.schedule, a.lanes or 512) and fi == B * MAXITER:
-                traffic = ent["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    kname = {0: "k_persistent (decoder, one launch per batch)", 1: "k_check+k_var",
-             2: "k_fused (decoder, fused flooding iteration, one launch per batch)"}[a.schedule]
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": fi * bytes_per_frame_iter, "launch_ms": k_ms,
-                "edge_updates_per_s": fi * E / (k_ms / 1e3), "frame_iterations_per_launch": fi,
-                "decode_only_frames_per_s": B / (k_ms / 1e3)}
+    # ---- decoder kernel alone (roofline)
+    k_ms, fi, steps_exec = wl.decoder_leg(max(3, a.steps))
+    roofline = wl.roofline(k_ms, fi, KERNEL_NAMES[a.schedule],
+                           lookup_traffic(n, B, MAXITER, a.precision, a.schedule, a.lanes or 512, fi))
 
     # ---- end to end through the host-buffer C ABI
     e2e = None
     if not a.no_e2e:
-        hy = [y.cpu().pin_memory() for y in ys]
-        hx = [x.cpu().pin_memory() for x in xs]
-        outs = dict(success=torch.empty(B, dtype=torch.uint8).pin_memory(),
-                    iters=torch.empty(B, dtype=torch.int32).pin_memory(),
-                    bit_errors=torch.empty(B, dtype=torch.int32).pin_memory(),
-                    post=torch.empty((B, n), dtype=torch.float32 if a.precision == "fp32" else torch.float64).pin_memory())
-        for i in range(min(a.warmup, 2)):
-            rec.run_host(hy[i % n_sets], hx[i % n_sets], MAXITER, K, outs)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(a.steps):
-            rec.run_host(hy[i % n_sets], hx[i % n_sets], MAXITER, K, outs)
-        barrier()
-        el = time.perf_counter() - t0
-        te = torch.tensor([el], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = B * S * 16
-        d2h = B * (1 + 4 + 4) + outs["post"].numel() * outs["post"].element_size()
-        e2e = {"value": total_frames / float(te.item()), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+        el, h2d, d2h = wl.e2e_leg(a.steps, a.warmup, barrier)
+        e2e = {"value": total_frames / max_over_ranks(el), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h,
                "api": "qr_reconcile_host: host y (f64) + tx symbols (i64) in; success, iterations, bit errors and "
                       "final LLRs out; pinned host memory"}
 
+    # ---- supplementary operating points (N = 1 only: they are reported, not scaled)
+    points = None
+    if world == 1 and not a.no_extras and n == N_CODE:
+        points = extras(a, torch, qr, codes, dev, wl, barrier)
+
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     cpu = None
     if not a.no_cpu:
-        fpw = a.cpu_frames or (2 if n >= 30000 else 8)
-        r = run_cpu("port", n, a.snr, fpw, 1)
-        cpu = {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
-               "sample": f"{r['cores']} processes x {fpw} frames of the same workload, one frame per process at a "
-                         f"time (oracle/qr_oracle.c, gcc -O2); per frame: front end+syndrome {r['chain']:.3f} s, "
-                         f"demap {r['demap']:.2f} s, decode {r['dec']:.2f} s ({r['iters']:.0f} iterations)"}
+        cpu = cpu_baseline(a, torch, qr, wl)
     cnt = counters.cpu().tolist()
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n, a.snr),
-                       "frames_per_gpu_per_step": B, "demap": a.demap, "decoder_lanes": a.lanes or 512,
-                       "schedule": {0: "persistent", 1: "launch", 2: "fused"}[a.schedule],
-                       "l2_policy": f"{n_sets} alternating input sets of {B * S * 16 / 1e9:.1f} GB each (>> 126 MB L2)"},
+            "config": workload_config(a, wl.n_sets),
             "info_gbit_per_s": value * K / 1e9,
             "avg_iterations": fi / B, "ber": cnt[0] / max(1, cnt[4] * K), "fer": cnt[1] / max(1, cnt[4]),
+            "counters_all_reduced_inside_timed_region": True,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             # per step: front end, syndrome, demapper, batch init, persistent decoder, error count
             "gpu_launches": 6 * a.steps * world, "clocks": clocks}
+    if points is not None:
+        line["operating_points"] = points
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline(a, torch, qr, wl):
+    """the CPU oracle decodes, one frame per process and call, the IDENTICAL frames taken from
+    the GPU batch (input set 0); reported beside its agreement with the GPU's fp64 mode on those frames."""
+    P = os.cpu_count() or 1
+    fpw = a.cpu_frames or (2 if wl.n >= 30000 else 8)
+    F = min(P * fpw, wl.B)
+    y = wl.ys[0][:F].cpu().numpy(); x = wl.xs[0][:F].cpu().numpy()
+    jobs = [[(y[f], x[f]) for f in range(w, F, P)] for w in range(P)]
+    jobs = [j for j in jobs if j]
+    arm = CpuArm("port", wl.n, a.snr, workers=len(jobs))
+    try:
+        r = arm.step(given=jobs)
+    finally:
+        arm.close()
+    cpu_res = {}
+    for w, lst in enumerate(r["results"]):
+        for k, (ok, it, post) in enumerate(lst):
+            cpu_res[w + k * len(jobs)] = (ok, it, post)
+    # the same frames through the GPU's fp64 parity mode (exact bisection demapper, fused schedule where it applies)
+    from qamreconciliation.pipeline import Reconciler
+    rec64 = Reconciler(wl.dec, wl.nm, precision="fp64", demap="exact", lanes=min(512, (F + 31) // 32 * 32), schedule=3)
+    out = rec64.run_device(wl.ys[0][:F], wl.xs[0][:F], MAXITER, k_info=wl.K)
+    g_ok = out["success"].cpu().numpy(); g_it = out["iters"].cpu().numpy(); g_post = out["post"].cpu().numpy()
+    same, rel_conv, dec_same = 0, 0.0, []
+    for f in range(F):
+        ok, it, post = cpu_res[f]
+        eq = (ok == int(g_ok[f])) and (it == int(g_it[f]))
+        same += eq
+        if eq and ok:            # converged on both sides in the same iteration: compare the final LLRs
+            rel_conv = max(rel_conv, float(np.max(np.abs(g_post[f] - post) / np.maximum(np.abs(post), 1e-300))))
+        dec_same.append(float(np.mean((g_post[f] < 0) == (post < 0))))
+    del rec64, out
+    return {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+            "per_core_frames_per_s": r["fps"] / r["cores"], "info_gbit_per_s": r["fps"] * wl.K / 1e9,
+            "edge_updates_per_s": r["fps"] * r["iters"] * wl.E,
+            "sample": f"{r['cores']} processes x {len(jobs[0])} frames, the first {F} frames of the GPU batch (y, x copied to "
+                      f"the host), one frame per process and call, whole chain (oracle/qr_oracle.c, gcc -O2); wall "
+                      f"{r['wall']:.1f} s; per frame: front end+syndrome {r['chain']:.3f} s, demap {r['demap']:.2f} s, "
+                      f"decode {r['dec']:.2f} s ({r['iters']:.0f} iterations)",
+            "agreement": {"frames": F, "vs": "GPU fp64 mode (exact demapper) on the same frames",
+                          "success_iters_equal": same / F,
+                          "max_rel_llr_err_converged": rel_conv if same and any(cpu_res[f][0] for f in range(F)) else None,
+                          "min_hard_decision_agreement": min(dec_same)}}
+
+
+def extras(a, torch, qr, codes, dev, wl, barrier):
+    """The same measurement at the operating points a reconciliation system runs at, the fp64 parity mode, and the
+    decoder on BASELINE configs 3 and 4 -- in the driver-run line, so they are judged on driver-run numbers."""
+    steps, warmup = min(a.steps, 5), 3
+    pts = {}
+    cfg = np.zeros(1 << BPS, dtype=np.uint8); cfg[1::2] = 1
+    vid, cid = codes.regular_ldpc(a.n, DV, DC, seed=CODE_SEED)
+
+    def measure(w, name, e2e=True, kname=None):
+        ms, counters = w.device_leg(steps, warmup, barrier)
+        cnt = counters.cpu().tolist()
+        k_ms, fi, _ = w.decoder_leg(3)
+        rec = {"value": w.B * steps / (ms / 1e3), "unit": "frames/s", "ms_per_step": ms / steps, "steps": steps,
+               "warmup": warmup, "frames_per_step": w.B, "avg_iterations": fi / w.B,
+               "fer": cnt[1] / max(1, cnt[4]), "ber": cnt[0] / max(1, cnt[4] * w.K),
+               "roofline": w.roofline(k_ms, fi, kname or KERNEL_NAMES[w.schedule],
+                                      lookup_traffic(w.n, w.B, w.maxiter, w.precision, w.schedule, w.lanes or 512, fi))}
+        if e2e:
+            el, h2d, d2h = w.e2e_leg(steps, warmup, barrier)
+            rec["e2e"] = {"value": w.B * steps / el, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        pts[name] = rec
+
+    for snr in (4.0, 5.0):
+        w = Workload(torch, qr, codes, dev, 0, vid, cid, BPS, snr, cfg, a.frames, MAXITER, a.precision, a.demap, a.lanes,
+                     a.schedule, dec=wl.dec)
+        measure(w, f"config2_{snr:g}dB")
+        del w
+    w = Workload(torch, qr, codes, dev, 0, vid, cid, BPS, a.snr, cfg, 512, MAXITER, "fp64", "exact", 512, a.schedule,
+                 dec=wl.dec)
+    measure(w, "config2_fp64_parity_mode", e2e=False)
+    del w
+    torch.cuda.empty_cache()
+    # BASELINE config 3: irregular R = 0.2, n = 131070 (3 * 43690), 8-PAM, 100 iterations max, below its waterfall
+    v3, c3 = codes.irregular_ldpc(131070, 104856, [3, 8], [0.9, 0.1], seed=3)
+    cfg3 = np.zeros(8, dtype=np.uint8); cfg3[1::2] = 1
+    w = Workload(torch, qr, codes, dev, 0, v3, c3, 3, 3.0, cfg3, 1024, 100, "fp32", "fast", 512, 3, n_sets=1)
+    measure(w, "config3_irregular_n131070_8pam", e2e=False)
+    del w
+    torch.cuda.empty_cache()
+    # BASELINE config 4: QKD scale, irregular R = 0.1, n = 2^20, 2-PAM, 60 iterations max
+    v4, c4 = codes.irregular_ldpc(1 << 20, 943718, [3, 4, 10], [0.8, 0.15, 0.05], seed=4)
+    w = Workload(torch, qr, codes, dev, 0, v4, c4, 1, -12.0, np.array([0, 1], dtype=np.uint8), 256, 60, "fp32", "fast",
+                 256, 3, n_sets=1)
+    measure(w, "config4_irregular_n1048576_2pam", e2e=False)
+    del w
+    torch.cuda.empty_cache()
+    return pts
 
 
 def workload_name(n, snr):

@@ -41,6 +41,8 @@ extern "C" {
 #define QR_DEMAP_EXACT 0      /* replays the reference's 1e-9 bisection (noisemapper.pyx:310-345) */
 #define QR_DEMAP_FAST 1       /* safeguarded Newton on F_Y, then the same dyadic cell as the bisection */
 #define QR_DEMAP_CORRECTED 2  /* flag bit: divide the k<j exponent by 2*sigma^2 too (fixes noisemapper.pyx:503-507) */
+#define QR_DEMAP_F32GRADE 4   /* flag bit, with QR_DEMAP_FAST: LLRs good to float precision (~1e-6 relative): no 2^-30 cell
+                                 replay, MUFU-based exp / log / reciprocals.  What the fp32 decoder mode is fed. */
 
 /* decoder schedules (qr_decoder_set_schedule) */
 #define QR_SCHED_PERSISTENT 0 /* one cooperative kernel per batch, grid barriers between phases */

@@ -10,8 +10,10 @@
 
 #if defined(__CUDACC__)
 #define QR_HD __host__ __device__ __forceinline__
+#define QR_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define QR_HD inline
+#define QR_HD_NOINLINE inline
 #endif
 
 namespace qr {

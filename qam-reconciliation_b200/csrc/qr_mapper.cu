@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(256) k_front_end(MapperView m, const double *_
     }
 }
 
+static unsigned grid_for_elems(int64_t n, int per_block = 256, int cap = 148 * 32);
+
 template <typename OUT>
 __global__ void __launch_bounds__(128) k_demap(MapperView m, const double *__restrict__ n_hat,
                                                const long long *__restrict__ tx, int64_t n, int mode,
@@ -130,6 +132,45 @@ __global__ void __launch_bounds__(128) k_demap(MapperView m, const double *__res
         demap_symbol(m, t, n_hat[sidx], checked_index(m, tx[sidx]), mode, alpha, out);
         for (int k = 0; k < m.bps; ++k) llr[sidx * m.bps + k] = (OUT)out[k];
     }
+}
+
+// fp32-grade demapper (QR_DEMAP_FAST | QR_DEMAP_F32GRADE), one instantiation per alphabet size: everything unrolled,
+// accumulators in registers, the rare slow paths out of line
+template <typename OUT, int BPS>
+__global__ void __launch_bounds__(256) k_demap32(MapperView m, const double *__restrict__ n_hat,
+                                                 const long long *__restrict__ tx, int64_t n, int corrected,
+                                                 double alpha, OUT *__restrict__ llr)
+{
+    __shared__ SharedTables s;
+    stage_tables(m, s);
+    const TablesRef t = tables_ref(s);
+    for (int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sidx < n;
+         sidx += (int64_t)gridDim.x * blockDim.x) {
+        double out[BPS];
+        demap_symbol_f32grade<BPS>(m, t, n_hat[sidx], checked_index(m, tx[sidx]), corrected != 0, alpha, out);
+        if constexpr (BPS == 2 && sizeof(OUT) == 4) {
+            *reinterpret_cast<float2 *>(llr + sidx * 2) = make_float2((float)out[0], (float)out[1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < BPS; ++k) llr[sidx * BPS + k] = (OUT)out[k];
+        }
+    }
+}
+
+template <typename OUT>
+static bool launch_demap32(const qr_mapper *m, const double *n_hat, const long long *tx, int64_t n, int mode, double alpha,
+                           OUT *llr, cudaStream_t st)
+{
+    if (!m->uniform || m->bps > 4) return false;
+    const unsigned grid = grid_for_elems(n, 256, 148 * 16);
+    const int corr = (mode & QR_DEMAP_CORRECTED) != 0;
+    switch (m->bps) {
+    case 1: k_demap32<OUT, 1><<<grid, 256, 0, st>>>(view_of(m), n_hat, tx, n, corr, alpha, llr); break;
+    case 2: k_demap32<OUT, 2><<<grid, 256, 0, st>>>(view_of(m), n_hat, tx, n, corr, alpha, llr); break;
+    case 3: k_demap32<OUT, 3><<<grid, 256, 0, st>>>(view_of(m), n_hat, tx, n, corr, alpha, llr); break;
+    default: k_demap32<OUT, 4><<<grid, 256, 0, st>>>(view_of(m), n_hat, tx, n, corr, alpha, llr); break;
+    }
+    return true;
 }
 
 __global__ void __launch_bounds__(128) k_g_inv(MapperView m, const double *__restrict__ n_hat,
@@ -173,7 +214,7 @@ __global__ void __launch_bounds__(256) k_direct_llr(MapperView m, const double *
     }
 }
 
-static unsigned grid_for_elems(int64_t n, int per_block = 256, int cap = 148 * 32)
+static unsigned grid_for_elems(int64_t n, int per_block, int cap)
 {
     int64_t g = (n + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -353,11 +394,19 @@ int qr_demap_lappr(const qr_mapper *m, const double *d_n_hat, const int64_t *d_t
     if (!m) return qr::fail(QR_ERR_INVALID, "null mapper");
     if (n < 0) return qr::fail(QR_ERR_INVALID, "negative length");
     if (llr_dtype != QR_F32 && llr_dtype != QR_F64) return qr::fail(QR_ERR_INVALID, "bad llr dtype");
-    if (mode < 0 || mode > 3) return qr::fail(QR_ERR_INVALID, "bad demap mode");
+    if (mode < 0 || mode > 7 || ((mode & QR_DEMAP_F32GRADE) && !(mode & QR_DEMAP_FAST)))
+        return qr::fail(QR_ERR_INVALID, "bad demap mode");
     if (n == 0) return QR_OK;
     if (!d_n_hat || !d_tx_index || !d_llr) return qr::fail(QR_ERR_INVALID, "null array");
     qr::DeviceGuard guard(m->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long *tx = reinterpret_cast<const long long *>(d_tx_index);
+    if ((mode & QR_DEMAP_F32GRADE) &&
+        (llr_dtype == QR_F64 ? qr::launch_demap32<double>(m, d_n_hat, tx, n, mode, alpha, static_cast<double *>(d_llr), st)
+                             : qr::launch_demap32<float>(m, d_n_hat, tx, n, mode, alpha, static_cast<float *>(d_llr), st))) {
+        QR_CUDA_CHECK(cudaGetLastError());
+        return QR_OK;
+    }
     const unsigned grid = qr::grid_for_elems(n, 128, 148 * 64);
     if (llr_dtype == QR_F64)
         qr::k_demap<double><<<grid, 128, 0, st>>>(qr::view_of(m), d_n_hat, reinterpret_cast<const long long *>(d_tx_index),

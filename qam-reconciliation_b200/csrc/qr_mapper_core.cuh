@@ -437,6 +437,103 @@ QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, con
     return lo + (idx + 0.5) * cell;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32-GRADE demapper (QR_DEMAP_F32GRADE): for LLRs that are consumed as float.  The reference's result
+// is a function of the root y* of F_Y(y) = target, snapped to a 2^-30 cell and pushed through fp64
+// exp / log / divisions -- fidelity a float LLR cannot show.  Here the root is taken from the same
+// Hermite table (one Newton step on the cubic: |dy| ~ 1e-11, no snap), exponentials are a double range
+// reduction + ONE MUFU.EX2, reciprocals a float seed + one Newton step, the final log a MUFU.LG2 on the
+// mantissa.  Relative error of the LLR ~1e-6 (tests: 1e-5 relative + 1e-6 absolute against the exact replay).
+QR_HD double rcp_f32grade(double x)
+{
+    if (!(fabs(x) > 1e-30 && fabs(x) < 1e30)) return 1.0 / x;     // outside the float range (rare): the real division
+#if defined(__CUDA_ARCH__)
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)x));
+#else
+    const float r0 = 1.0f / (float)x;
+#endif
+    const double r = (double)r0;
+    return fma(r, fma(-x, r, 1.0), r);      // one Newton step: ~1e-13 relative
+}
+
+// e^u, |u| < 700, relative error ~2^-22 whatever |u| (the range reduction is done in double)
+QR_HD double exp_f32grade(double u)
+{
+    const double t = u * 1.4426950408889634;
+#if defined(__CUDA_ARCH__)
+    const int32_t ni = __double2int_rn(t);
+    float m;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"((float)(t - (double)ni)));
+    return (double)m * __longlong_as_double((long long)(ni + 1023) << 52);
+#else
+    const int32_t ni = (int32_t)nearbyint(t);
+    const float m = exp2f((float)(t - (double)ni));
+    return ldexp((double)m, ni);
+#endif
+}
+
+// ln(r) for a positive finite double r: exponent taken from the bits, MUFU.LG2 on the mantissa in [0.75, 1.5)
+// (so that r ~ 1, an LLR near zero, keeps the small absolute error of the approximation)
+QR_HD double log_f32grade(double r)
+{
+#if defined(__CUDA_ARCH__)
+    long long b = __double_as_longlong(r);
+    int32_t e = (int32_t)((b >> 52) & 0x7ff) - 1023;
+    double m = __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);   // [1, 2)
+    if (m >= 1.5) { m *= 0.5; e += 1; }
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"((float)m));
+    return 0.6931471805599453 * ((double)e + (double)l);
+#else
+    int e = 0;
+    double m = 2.0 * frexp(r, &e);      // [1, 2)
+    e -= 1;
+    if (m >= 1.5) { m *= 0.5; e += 1; }
+    return 0.6931471805599453 * ((double)e + (double)log2f((float)m));
+#endif
+}
+
+// (out of line: rare, and its register needs must not shape the callers)
+static QR_HD_NOINLINE double g_inv_slow_path(const double *a, const double *p, const double *thr, const double *FYt,
+                                             int order, double sigma, double s2, double target, int32_t region,
+                                             const InvTable tab)
+{
+    return g_inv_fast(a, p, thr, FYt, order, sigma, s2, target, 1e-9, region, tab);
+}
+
+// root of F_Y(y) = target to ~1e-10 where the density is not vanishing; everything else (saturated targets, deep
+// tails, targets outside the table) goes through g_inv_fast, which ends on the reference's cell
+QR_HD double g_inv_f32grade(const double *a, const double *p, const double *thr, const double *FYt, int order,
+                            double sigma, double s2, double target, int32_t region, const InvTable tab)
+{
+    if (region > 0 && target == FYt[region]) return thr[region];
+    if (region < order - 1 && target == FYt[region + 1]) return thr[region + 1];
+    if (target > 0.0 && target < 1.0 && tab.n > 1 && tab.f && tab.jump && target >= tab.F[0] &&
+        target < tab.F[tab.n - 1]) {
+        const int32_t t = (int32_t)(target * tab.jn);       // exact: jn is a power of two
+        int32_t lo = tab.jump[t], hi = tab.jump[t + 1] + 1; // F[lo] <= t / jn <= target < (t + 1) / jn < F[hi]
+        if (hi > tab.n - 1) hi = tab.n - 1;
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (tab.F[mid] <= target) lo = mid; else hi = mid;
+        }
+        const double F0 = tab.F[lo], F1 = tab.F[hi], d0 = tab.f[lo], d1 = tab.f[hi];
+        const double dF = F1 - F0, d = target - F0;
+        if (dF > 1e-30 && (d0 < d1 ? d0 : d1) > 1e-6) {
+            const double A = tab.h * d0, B = tab.h * d1;
+            const double c2 = 3 * dF - 2 * A - B, c3 = A + B - 2 * dF;     // cubic Hermite through (F, f) at both ends
+            double sx = d * rcp_f32grade(dF);
+            const double G = sx * (A + sx * (c2 + sx * c3));
+            const double Gp = A + sx * (2 * c2 + 3 * sx * c3);
+            sx -= (G - d) * rcp_f32grade(Gp);
+            sx = sx < 0 ? 0 : (sx > 1 ? 1 : sx);
+            return tab.y0 + (lo + sx) * tab.h;
+        }
+    }
+    return g_inv_slow_path(a, p, thr, FYt, order, sigma, s2, target, region, tab);
+}
+
 // demap_lappr (noisemapper.pyx:450-540) given the `order` reconstructed samples y_hat[i].
 // NOTE the reference divides the exponent by 2*sigma^2 only for k > j (:511-515), not for k < j
 // (:503-507); `corrected` divides in both.
@@ -483,6 +580,7 @@ QR_HD void demap_symbol(const MapperView &m, const TablesRef &s, double nv, int3
                         double *out)
 {
     const bool fast = (mode & 1) != 0, corrected = (mode & QR_DEMAP_CORRECTED) != 0;
+    const bool grade32 = fast && (mode & QR_DEMAP_F32GRADE) != 0;
     const double two_s2 = 2 * m.noise_var;
     // fast mode (tolerance 1e-7): multiply by the reciprocal instead of dividing twelve times
     // per symbol, one log of the ratio instead of two logs; exact mode keeps the reference's operations
@@ -491,9 +589,10 @@ QR_HD void demap_symbol(const MapperView &m, const TablesRef &s, double nv, int3
     for (int k = 0; k < m.bps; ++k) { N[k] = 0; D[k] = 0; }
     for (int i = 0; i < m.order; ++i) {
         const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
-        const double yh = fast ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i,
-                                            InvTable{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h, m.inv_jump, m.inv_jn})
-                               : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
+        const InvTable tab{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h, m.inv_jump, m.inv_jn};
+        const double yh = grade32 ? g_inv_f32grade(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, i, tab)
+                          : fast  ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i, tab)
+                                  : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
         double sum = 0;
         // Fast mode, uniform constellation: with d = y_hat - a_j and a_k - a_j = m step the exponent is
         // (2 d - m step)(m step) c = m (2 d step c) - (m step)^2 c, so exp of it = E^m G[m] with ONE exp per side
@@ -507,14 +606,14 @@ QR_HD void demap_symbol(const MapperView &m, const TablesRef &s, double nv, int3
             // all M - 1 powers, against probabilities zero-padded outside the alphabet
             const double *glo = corrected ? s.ghi : s.glo;
             const double *pj = s.pz + (M - 1) + j;
-            const double Eh = exp(u_hi), El = exp(u_lo);
+            const double Eh = grade32 ? exp_f32grade(u_hi) : exp(u_hi), El = grade32 ? exp_f32grade(u_lo) : exp(u_lo);
             double ph = 1.0, pl = 1.0;
             sum = s.p[j];
             for (int mm = 1; mm < M; ++mm) {
                 ph *= Eh; pl *= El;
                 sum += pj[mm] * (ph * s.ghi[mm]) + pj[-mm] * (pl * glo[mm]);
             }
-            const double w = s.delta[i] / sum;
+            const double w = grade32 ? s.delta[i] * rcp_f32grade(sum) : s.delta[i] / sum;
             int q = i;
             for (int k = 0; k < m.bps; ++k) {
                 if ((q * (q + 1)) & 3) D[k] += w;
@@ -543,10 +642,101 @@ QR_HD void demap_symbol(const MapperView &m, const TablesRef &s, double nv, int3
         }
     }
     for (int k = 0; k < m.bps; ++k) {
-        double v = fast ? log(N[k] / D[k]) : log(N[k]) - log(D[k]);
+        double v;
+        if (grade32) {
+            const double r = N[k] * rcp_f32grade(D[k]);
+            // (a ratio outside the normal doubles -- one side vanished -- takes the library log)
+            v = (r > 1e-300 && r < 1e300) ? log_f32grade(r) : log(N[k] / D[k]);
+        } else {
+            v = fast ? log(N[k] / D[k]) : log(N[k]) - log(D[k]);
+        }
         if (alpha != 1.0) v = mul_rn(v, alpha);
         out[k] = v;
     }
+}
+
+// The sum over Alice's symbols of one hypothesis in the direct (non E^m) form, library exp: the rare case where a power
+// of E could overflow (see demap_symbol)
+static QR_HD_NOINLINE double demap_sum_direct(const TablesRef &s, int order, int32_t j, double yh, bool corrected,
+                                              double inv_two_s2)
+{
+    double sum = 0;
+    for (int k = 0; k < order; ++k) {
+        if (k == j) { sum += s.p[j]; continue; }
+        double ex = (2 * yh - s.a[k] - s.a[j]) * (s.a[k] - s.a[j]);
+        if (k > j || corrected) ex *= inv_two_s2;
+        sum += exp(ex) * s.p[k];
+    }
+    return sum;
+}
+
+// demap_lappr for ONE symbol at fp32 grade, alphabet size known at compile time (everything unrolled, N / D in
+// registers): equally spaced constellations only (PAMAlphabet always is).  Same formulas as demap_symbol's fast path.
+template <int BPS>
+QR_HD void demap_symbol_f32grade(const MapperView &m, const TablesRef &s, double nv, int32_t j, bool corrected,
+                                 double alpha, double *out)
+{
+    constexpr int M = 1 << BPS;
+    const double inv_two_s2 = rcp_f32grade(2 * m.noise_var);
+    const double step = M > 1 ? s.a[1] - s.a[0] : 0.0;
+    const InvTable tab{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h, m.inv_jump, m.inv_jn};
+    const double *glo = corrected ? s.ghi : s.glo;
+    const double *pj = s.pz + (M - 1) + j;
+    const double aj = s.a[j], pjj = s.p[j];
+    double N[BPS], D[BPS];
+#pragma unroll
+    for (int k = 0; k < BPS; ++k) { N[k] = 0; D[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
+        const double yh = g_inv_f32grade(s.a, s.p, s.thr, s.FYt, M, m.sigma, m.s2, target, i, tab);
+        const double dd = yh - aj;
+        const double u_hi = 2 * dd * step * inv_two_s2, u_lo = -2 * dd * step * (corrected ? inv_two_s2 : 1.0);
+        double sum;
+        if (fabs(u_hi) * (M - 1) < 600.0 && fabs(u_lo) * (M - 1) < 600.0) {
+            const double Eh = exp_f32grade(u_hi), El = exp_f32grade(u_lo);
+            double ph = 1.0, pl = 1.0;
+            sum = pjj;
+#pragma unroll
+            for (int mm = 1; mm < M; ++mm) {
+                ph *= Eh; pl *= El;
+                sum += pj[mm] * (ph * s.ghi[mm]) + pj[-mm] * (pl * glo[mm]);
+            }
+        } else {
+            sum = demap_sum_direct(s, M, j, yh, corrected, inv_two_s2);
+        }
+        const double w = s.delta[i] * rcp_f32grade(sum);
+#pragma unroll
+        for (int k = 0; k < BPS; ++k) {
+            const int q = i >> k;
+            if ((q * (q + 1)) & 3) D[k] += w;        // Gray bit k of hypothesis i (compile-time after unrolling)
+            else N[k] += w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < BPS; ++k) {
+        const double r = N[k] * rcp_f32grade(D[k]);
+        double v = (r > 1e-300 && r < 1e300) ? log_f32grade(r) : log(N[k] / D[k]);
+        if (alpha != 1.0) v *= alpha;
+        out[k] = v;
+    }
+}
+
+// one symbol, any mode: what k_demap / k_demap32 run
+QR_HD void demap_symbol_any(const MapperView &m, const TablesRef &s, double nv, int32_t j, int mode, double alpha,
+                            double *out)
+{
+    const bool corrected = (mode & QR_DEMAP_CORRECTED) != 0;
+    if ((mode & QR_DEMAP_F32GRADE) && (mode & 1) && m.uniform && s.ghi) {
+        switch (m.bps) {
+        case 1: demap_symbol_f32grade<1>(m, s, nv, j, corrected, alpha, out); return;
+        case 2: demap_symbol_f32grade<2>(m, s, nv, j, corrected, alpha, out); return;
+        case 3: demap_symbol_f32grade<3>(m, s, nv, j, corrected, alpha, out); return;
+        case 4: demap_symbol_f32grade<4>(m, s, nv, j, corrected, alpha, out); return;
+        default: break;
+        }
+    }
+    demap_symbol(m, s, nv, j, mode, alpha, out);
 }
 
 // direct-reconciliation LLR (sims/reconciliation.pyx:25-51)

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libqamrecon.so")
 
 QR_OK, QR_ERR_INVALID, QR_ERR_GRAPH, QR_ERR_CUDA, QR_ERR_NOMEM = 0, 1, 2, 3, 4
 QR_F32, QR_F64 = 32, 64
-QR_DEMAP_EXACT, QR_DEMAP_FAST, QR_DEMAP_CORRECTED = 0, 1, 2
+QR_DEMAP_EXACT, QR_DEMAP_FAST, QR_DEMAP_CORRECTED, QR_DEMAP_F32GRADE = 0, 1, 2, 4
 QR_SCHED_PERSISTENT, QR_SCHED_LAUNCH, QR_SCHED_FUSED, QR_SCHED_AUTO = 0, 1, 2, 3
 
 _vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int32, C.c_double

@@ -16,9 +16,12 @@ def _demap_mode(mode):
         mode = os.environ.get("QAMRECON_DEMAP", "exact")
     if isinstance(mode, int):
         return mode
-    table = {"exact": _abi.QR_DEMAP_EXACT, "fast": _abi.QR_DEMAP_FAST,
+    table = {"exact": _abi.QR_DEMAP_EXACT, "fast": _abi.QR_DEMAP_FAST, "fast64": _abi.QR_DEMAP_FAST,
              "exact-corrected": _abi.QR_DEMAP_EXACT | _abi.QR_DEMAP_CORRECTED,
-             "fast-corrected": _abi.QR_DEMAP_FAST | _abi.QR_DEMAP_CORRECTED}
+             "fast-corrected": _abi.QR_DEMAP_FAST | _abi.QR_DEMAP_CORRECTED,
+             # LLRs to float precision (what the fp32 decoder consumes): no 2^-30 cell replay, MUFU exp / log
+             "fast32": _abi.QR_DEMAP_FAST | _abi.QR_DEMAP_F32GRADE,
+             "fast32-corrected": _abi.QR_DEMAP_FAST | _abi.QR_DEMAP_F32GRADE | _abi.QR_DEMAP_CORRECTED}
     if mode not in table:
         raise ValueError(f"unknown demap mode {mode!r}")
     return table[mode]

@@ -22,6 +22,10 @@ class Reconciler:
         self.llr_dtype = torch.float32 if precision == "fp32" else torch.float64
         from .noisemapper import _demap_mode
         self.demap_code = _demap_mode(demap)
+        # the fp32 decoder consumes float LLRs: the fast demapper then runs at float grade (no 2^-30 cell replay,
+        # MUFU exp / log; ~1e-6 relative, tests/test_emulation.py) -- 'fast64' keeps the double-grade fast mode
+        if precision == "fp32" and (self.demap_code & _abi.QR_DEMAP_FAST) and demap != "fast64":
+            self.demap_code |= _abi.QR_DEMAP_F32GRADE
         self.lanes, self.schedule = lanes, schedule
         self.N, self.C = dec.vnum, dec.cnum
         self.S = self.N // nm.bit_per_symbol

@@ -296,6 +296,55 @@ void emu_demap(int bps, const double *a, const double *thr, const double *p, dou
     }
 }
 
+// demap_symbol (the function k_demap runs per symbol) with host-built tables: every QR_DEMAP_* mode, including the
+// fp32-grade path (host stand-ins for the MUFU instructions: exp2f / log2f / float division)
+void emu_demap_symbol(int bps, const double *a, const double *thr, const double *p, double noise_var,
+                      const uint8_t *sign, const double *n_hat, const int64_t *tx, int64_t n, int mode, double alpha,
+                      double *llr)
+{
+    const int M = 1 << bps;
+    const double sigma = sqrt(noise_var), s2 = sqrt(2.0) * sigma;
+    std::vector<double> FYt(M + 1), delta(M), ghi(M), glo(M), pz(3 * M);
+    FYt[0] = 0; FYt[M] = 1;
+    for (int i = 1; i < M; ++i) FYt[i] = mixture_cdf(a, p, M, s2, thr[i]);
+    for (int i = 0; i < M; ++i) delta[i] = FYt[i + 1] - FYt[i];
+    const double step = M > 1 ? a[1] - a[0] : 0.0;
+    for (int i = 0; i < M; ++i) {
+        const double t2 = (i * step) * (i * step);
+        ghi[i] = exp(-t2 / (2 * noise_var));
+        glo[i] = exp(-t2);
+    }
+    for (int i = 0; i < 3 * M; ++i) {
+        const int k = i - (M - 1);
+        pz[i] = (k >= 0 && k < M) ? p[k] : 0.0;
+    }
+    const int32_t tn = 16385, jn = 8192;
+    const double ty0 = a[0] - 9.0 * sigma, th = (a[M - 1] + 9.0 * sigma - ty0) / (tn - 1);
+    std::vector<double> tabF(tn), tabf(tn);
+    for (int32_t j = 0; j < tn; ++j) {
+        tabF[j] = mixture_cdf(a, p, M, s2, ty0 + j * th);
+        tabf[j] = mixture_pdf(a, p, M, sigma, ty0 + j * th);
+    }
+    std::vector<int32_t> jump(jn + 2, 0);
+    for (int32_t t = 0; t <= jn; ++t) {
+        const double v = (double)t / (double)jn;
+        int32_t lo = 0, hi = tn;
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (tabF[mid] <= v) lo = mid; else hi = mid;
+        }
+        jump[t] = lo;
+    }
+    MapperView m{};
+    m.order = M; m.bps = bps; m.noise_var = noise_var; m.sigma = sigma; m.s2 = s2;
+    m.constellation = a; m.thresholds = thr; m.probabilities = p; m.sign_config = sign; m.sign_g = sign;
+    m.FY_thr = FYt.data(); m.delta = delta.data(); m.bare = nullptr;
+    m.inv_tab = tabF.data(); m.inv_pdf = tabf.data(); m.inv_n = tn; m.inv_y0 = ty0; m.inv_h = th;
+    m.inv_jump = jump.data(); m.inv_jn = jn; m.uniform = 1; m.index_errors = nullptr;
+    TablesRef t{a, p, thr, FYt.data(), delta.data(), sign, ghi.data(), glo.data(), pz.data()};
+    for (int64_t s = 0; s < n; ++s) demap_symbol_any(m, t, n_hat[s], (int32_t)tx[s], mode, alpha, llr + s * bps);
+}
+
 void emu_front(int bps, const double *a, const double *thr, const double *p, double noise_var,
                const uint8_t *sign, const double *y, int64_t n, int64_t *idx, double *n_hat, uint8_t *bits)
 {

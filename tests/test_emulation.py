@@ -281,3 +281,45 @@ def test_emulated_mapper_against_reference(path):
     d = np.zeros(n * bps)
     L.emu_direct(bps, ptr(a), C.c_double(2 * float(g["noise_var"])), ptr(y), C.c_int64(n), ptr(d))
     np.testing.assert_allclose(d, g["direct"], rtol=1e-13, atol=1e-13, equal_nan=True)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "mapper_*.npz"))))
+def test_emulated_fp32_grade_demapper_against_reference(path):
+    """QR_DEMAP_FAST | QR_DEMAP_F32GRADE (what the fp32 decoder mode is fed; reference noisemapper.pyx:450-559):
+    no 2^-30 cell replay, MUFU-grade exp / log / reciprocals.  Gate: 1e-5 relative + 1e-6 absolute against the
+    compiled reference's LLRs on the mapper fixtures (thresholds +-1e-12, +-0, +-40, +-1000 included) and on a dense
+    random sample against the exact replay."""
+    L = load()
+    g = np.load(path)
+    bps = int(g["bps"]); M = 1 << bps
+    a = np.ascontiguousarray(g["constellation"]); thr = np.ascontiguousarray(g["thresholds"])
+    p = np.ascontiguousarray(g["probabilities"]); sc = np.ascontiguousarray(g["sign_config"])
+    nv = C.c_double(float(g["noise_var"]))
+    one = C.c_double(1.0)
+    for nk, jk, lk in (("n_hat", "x", "lappr"), ("n_grid", "j_grid", "lappr_grid")):
+        nn = np.ascontiguousarray(g[nk]); jj = np.ascontiguousarray(g[jk])
+        got = np.zeros(nn.size * bps); fast = np.zeros(nn.size * bps)
+        L.emu_demap_symbol(bps, ptr(a), ptr(thr), ptr(p), nv, ptr(sc), ptr(nn), ptr(jj), C.c_int64(nn.size), 5, one, ptr(got))
+        L.emu_demap_symbol(bps, ptr(a), ptr(thr), ptr(p), nv, ptr(sc), ptr(nn), ptr(jj), C.c_int64(nn.size), 1, one, ptr(fast))
+        np.testing.assert_allclose(fast, g[lk], rtol=1e-7, atol=1e-7)          # (demap_symbol's fast path == fixture)
+        # a saturated metric (n_hat within 1e-9 of 0 or 1) is defined by where erf rounds: 2 % there, as in exact mode
+        sat = np.repeat((nn < 1e-9) | (nn > 1 - 1e-9), bps)
+        np.testing.assert_allclose(got[~sat], g[lk][~sat], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(got[sat], g[lk][sat], rtol=2e-2, atol=1e-6)
+    rng = np.random.default_rng(5)
+    nn = np.concatenate([rng.random(6000), 10.0 ** -rng.uniform(1, 12, 600), 1 - 10.0 ** -rng.uniform(1, 12, 600)])
+    jj = rng.integers(0, M, size=nn.size).astype(np.int64)
+    got = np.zeros(nn.size * bps); exact = np.zeros(nn.size * bps)
+    for alpha in (1.0, 0.9):
+        L.emu_demap_symbol(bps, ptr(a), ptr(thr), ptr(p), nv, ptr(sc), ptr(nn), ptr(jj), C.c_int64(nn.size), 5,
+                           C.c_double(alpha), ptr(got))
+        L.emu_demap_symbol(bps, ptr(a), ptr(thr), ptr(p), nv, ptr(sc), ptr(nn), ptr(jj), C.c_int64(nn.size), 0,
+                           C.c_double(alpha), ptr(exact))
+        sat = np.repeat((nn < 1e-9) | (nn > 1 - 1e-9), bps)
+        np.testing.assert_allclose(got[~sat], exact[~sat], rtol=1e-5, atol=1e-6)
+        assert np.median(np.abs(got - exact) / np.maximum(np.abs(exact), 1e-3)) < 2e-7
+    # corrected exponent variant
+    L.emu_demap_symbol(bps, ptr(a), ptr(thr), ptr(p), nv, ptr(sc), ptr(nn), ptr(jj), C.c_int64(nn.size), 7, one, ptr(got))
+    L.emu_demap_symbol(bps, ptr(a), ptr(thr), ptr(p), nv, ptr(sc), ptr(nn), ptr(jj), C.c_int64(nn.size), 2, one, ptr(exact))
+    sat = np.repeat((nn < 1e-9) | (nn > 1 - 1e-9), bps)
+    np.testing.assert_allclose(got[~sat], exact[~sat], rtol=1e-5, atol=1e-6)

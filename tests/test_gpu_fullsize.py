@@ -10,9 +10,12 @@ compiled reference by tests/test_oracle_golden.py), reference: Decoder._decode, 
     exact, posteriors to 1e-9 relative;
   * the fp32 fast mode on the same inputs: same success flags, same hard decisions on the converged frames.
 
-Tolerances: 1e-9 relative + 1e-9 absolute on posteriors (CUDA exp/log differ from glibc in the last ulp; a frame
-that runs to the iteration limit WITHOUT converging amplifies that ulp chaotically, so for such frames the bar is
-the one a user can observe: >= 99.9 % equal hard decisions and posteriors within 1e-6 on the bits that agree).
+Tolerances: 1e-9 relative + 1e-9 absolute on posteriors (CUDA exp/log differ from glibc in the last ulp).  A frame
+that runs to the iteration limit WITHOUT converging is a chaotic iteration: it amplifies that ulp exponentially
+(measured on B200: config 2 after 50 iterations still < 1e-6, config 4 after 60 iterations 4e-5, config 3 after 100
+iterations 3e-2).  For such frames the final posteriors get the bar a user can observe -- >= 99.9 % equal hard
+decisions -- and the 1e-9 bar is applied where it is meaningful: the same frame decoded with a limit of 8 iterations
+on both sides (flags, iteration counts and posteriors), i.e. before the amplification.
 """
 import os
 from concurrent.futures import ThreadPoolExecutor
@@ -48,7 +51,10 @@ def oracle_chain(orc, vid, cid, bps, cfg, n0, x, y, maxiter):
         llr = nm.demap_lappr_array(nh, x[f])
         synd = mat.eval_syndrome(word)
         ok, it, post = dec.decode(llr, synd, maxiter)
-        return dict(xh=xh, word=word, nh=nh, llr=llr, synd=synd, ok=int(ok), it=int(it), post=post)
+        early = None
+        if not ok:       # see the module docstring: the 1e-9 comparison of a non-converging frame is made after 8 iterations
+            early = dec.decode(llr, synd, 8)
+        return dict(xh=xh, word=word, nh=nh, llr=llr, synd=synd, ok=int(ok), it=int(it), post=post, early=early)
 
     with ThreadPoolExecutor(max_workers=min(len(x), os.cpu_count() or 1)) as pool:
         return list(pool.map(one, range(len(x))))
@@ -70,7 +76,11 @@ def compare_decoder(qr, dec, want, maxiter, schedules, lanes):
             else:
                 same = (post[f] < 0) == (w_post[f] < 0)
                 assert same.mean() >= 0.999, (sched, f, same.mean())
-                np.testing.assert_allclose(post[f][same], w_post[f][same], rtol=1e-6, atol=1e-6)
+                e_ok, e_it, e_post = want[f]["early"]
+                ok8, it8, post8 = dec.decode_batch(llr[f:f + 1], synd[f:f + 1], 8, precision="fp64", schedule=sched, lanes=lanes)
+                assert (int(ok8[0]), int(it8[0])) == (int(e_ok), int(e_it))
+                np.testing.assert_allclose(post8[0].cpu().numpy(), e_post, rtol=1e-9, atol=1e-9,
+                                           err_msg=f"schedule {sched} frame {f}, 8 iterations")
     # fp32 fast mode on the same inputs
     for sched in schedules:
         ok32, it32, post32 = dec.decode_batch(llr.float(), synd, maxiter, precision="fp32", schedule=sched, lanes=lanes)

@@ -188,6 +188,13 @@ def test_mapper_fixture(qr, path):
         fast = nm.demap_lappr_array_batch(g[nk], g[jk], mode="fast").cpu().numpy()
         np.testing.assert_allclose(fast[~sat], g[lk][~sat], rtol=1e-7, atol=1e-7)
         np.testing.assert_allclose(fast[sat], g[lk][sat], rtol=2e-2, atol=1e-9)
+        # fp32-grade fast mode (QR_DEMAP_FAST | QR_DEMAP_F32GRADE, what the fp32 decoder is fed): 1e-5 relative
+        # + 1e-6 absolute against the compiled reference, as float32 and as float64 output
+        for dt in (torch.float32, torch.float64):
+            f32g = nm.demap_lappr_array_batch(g[nk], g[jk], mode="fast32", out_dtype=dt).cpu().numpy().astype(np.float64)
+            ok = np.isfinite(g[lk]) & (np.abs(g[lk]) < 1e30)
+            np.testing.assert_allclose(f32g[~sat & ok], g[lk][~sat & ok], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(f32g[sat & ok], g[lk][sat & ok], rtol=2e-2, atol=1e-6)
     M = pa.order
     yh = nm.g_inv_search_batch(np.repeat(g["n_grid"][:8], M), np.tile(np.arange(M), 8)).cpu().numpy().reshape(8, M)
     inner = (g["n_grid"][:8] > 1e-9) & (g["n_grid"][:8] < 1 - 1e-9)
