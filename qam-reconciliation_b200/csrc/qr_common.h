@@ -63,8 +63,8 @@ struct qr_graph {
     // so a warp runs one unrolled code path; empty when every variable has the same degree
     std::vector<int32_t> var_work;   // [N]
     int32_t *d_var_work = nullptr;
-    // fused schedule (var_deg == 3 only): per CSR slot {variable | own position << 28, the variable's three
-    // CSR slots in ascending edge id}; empty otherwise
+    // fused schedule: per CSR slot a 16-byte neighbour record (Nbr4, qr_decode_fused.cuh); empty when the graph is
+    // outside its limits (2^27 variables, variable degree 64)
     std::vector<int32_t> slot_nbr;   // [4 * E]
     int32_t *d_slot_nbr = nullptr;
     // device copies

@@ -354,8 +354,6 @@ __global__ void k_init_batch(LaneState *st0, LaneState *st1, int32_t *unsat0, in
         ctrl[CTRL_FIN_STEP] = -1;
         ctrl[CTRL_REFILL_CNT + 0] = (int32_t)min((int64_t)lanes, frames);
         ctrl[CTRL_REFILL_CNT + 1] = 0;
-        ctrl[6] = 0;   // CTRL_ARRIVE of the fused schedule
-        ctrl[7] = 0x7fffffff; ctrl[8] = 0x7fffffff;   // CTRL_MINFIN, CTRL_MINFIN_NEXT
         stats[0] = 0;
         stats[1] = 0;
     }
@@ -467,11 +465,12 @@ static int run_batch_t(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t str
 template <typename T>
 int run_batch_fused(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream);   // qr_decode_fused.cu
 bool fused_eligible(const qr_graph *g);
+bool fused_preferred(const qr_graph *g, size_t w);
 
 template <typename T>
 static int run_batch(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream)
 {
-    if (d->schedule == QR_SCHED_FUSED || (d->schedule == QR_SCHED_AUTO && fused_eligible(d->g)))
+    if (d->schedule == QR_SCHED_FUSED || (d->schedule == QR_SCHED_AUTO && fused_preferred(d->g, sizeof(T))))
         return run_batch_fused<T>(d, P, stream);
     if constexpr (sizeof(T) == 4) {
         // narrower lane vectors (more, lighter threads) -- experimental, QAMRECON_VEC=1|2
@@ -527,10 +526,9 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
         if (const char *v = getenv("QAMRECON_VEC")) d->vec = atoi(v);
         if (const char *v = getenv("QAMRECON_FUSED_TILE")) d->fused_tile = atoi(v);
         if (const char *v = getenv("QAMRECON_FUSED_HINTS")) d->fused_hints = atoi(v);
-        if (const char *v = getenv("QAMRECON_FUSED_PIPE")) d->fused_pipe = atoi(v);
-        if (const char *v = getenv("QAMRECON_FUSED_PREFETCH")) d->fused_prefetch = atoi(v);
         if (const char *v = getenv("QAMRECON_FUSED_RPC")) d->fused_rpc = atoi(v);
-        if (const char *v = getenv("QAMRECON_FUSED_STATIC")) d->fused_static = atoi(v);
+        if (const char *v = getenv("QAMRECON_FUSED_PP_ITEMS")) d->fused_pp_items = atoi(v);
+        if (const char *v = getenv("QAMRECON_FUSED_LEAN")) d->fused_lean = atoi(v);
         if (const char *v = getenv("QAMRECON_FUSED_STORE_POST")) d->fused_store_post = atoi(v);
         const size_t L = (size_t)lanes;
         QR_CUDA_CHECK(cudaMalloc(&d->c2v, (size_t)g->E * L * w));
@@ -543,8 +541,6 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
         QR_CUDA_CHECK(cudaMalloc((void **)&d->stats, 2 * sizeof(unsigned long long)));
         QR_CUDA_CHECK(cudaMalloc((void **)&d->work, 2 * qr::kMaxLaneTiles * sizeof(int32_t)));
         QR_CUDA_CHECK(cudaMalloc((void **)&d->refill_list, 2 * L * sizeof(int32_t)));
-        QR_CUDA_CHECK(cudaMalloc((void **)&d->postok, 2 * L * sizeof(int32_t)));
-        QR_CUDA_CHECK(cudaMemset(d->postok, 0, 2 * L * sizeof(int32_t)));
         QR_CUDA_CHECK(cudaMemset(d->c2v, 0, (size_t)g->E * L * w));
         QR_CUDA_CHECK(cudaMemset(d->post, 0, (size_t)g->N * L * w));
         QR_CUDA_CHECK(cudaMemset(d->llr, 0, (size_t)g->N * L * w));
@@ -569,7 +565,7 @@ void qr_decoder_destroy(qr_decoder *d)
     cudaGetDevice(&prev);
     cudaSetDevice(d->device);
     cudaFree(d->c2v); cudaFree(d->c2v2); cudaFree(d->post); cudaFree(d->llr); cudaFree(d->synd);
-    cudaFree(d->st); cudaFree(d->unsat); cudaFree(d->ctrl); cudaFree(d->stats); cudaFree(d->work); cudaFree(d->refill_list); cudaFree(d->postok);
+    cudaFree(d->st); cudaFree(d->unsat); cudaFree(d->ctrl); cudaFree(d->stats); cudaFree(d->work); cudaFree(d->refill_list); cudaFree(d->fused_ctl); cudaFree(d->fused_rlist); cudaFree(d->fused_ppq); cudaFree(d->fused_nbrl);
     cudaFree(d->pipe_buf);
     cudaFree(d->dev_buf);
     if (d->pipe_streams_ready) {
@@ -590,7 +586,7 @@ int qr_decoder_set_schedule(qr_decoder *d, int schedule)
         schedule != QR_SCHED_AUTO)
         return qr::fail(QR_ERR_INVALID, "unknown schedule");
     if (schedule == QR_SCHED_FUSED && !qr::fused_eligible(d->g))
-        return qr::fail(QR_ERR_INVALID, "fused schedule needs every variable of degree 3 and check degrees <= 8");
+        return qr::fail(QR_ERR_INVALID, "fused schedule needs check degrees <= 8, variable degrees 1..64 and fewer than 2^27 variables");
     d->schedule = schedule;
     return QR_OK;
 }

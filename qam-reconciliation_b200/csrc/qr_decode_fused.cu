@@ -1,13 +1,11 @@
-// QR_SCHED_FUSED: persistent cooperative kernel running the fused flooding iteration of
-// qr_decode_fused.cuh (reference: Decoder._decode, decoder.pyx:391-436).
+// QR_SCHED_FUSED: persistent kernel running the fused flooding iteration of qr_decode_fused.cuh as a TILE
+// PIPELINE (reference: Decoder._decode, decoder.pyx:391-436; the stream of work items, BK and PP are described
+// at the top of qr_decode_fused.cuh).
 //
-// One step = fused phase (all tiles, work-stealing claims handed out in tile order so the grid sweeps
-// one L2-sized tile at a time) -> the LAST CTA to finish it advances the lane state machine for all lanes
-// -> grid barrier -> (only if a frame finished) refill phase -> grid barrier.
-//
-// Thread mapping of the fused phase: bx = TL / VEC threads share a check (together they move one contiguous
-// TL * w byte row per access), a warp is 32 / bx checks wide, and WARPS claim work from one counter (see
-// fused_phase); fp32: 128 registers, two CTAs of 256 threads per SM.
+// Thread mapping of a sweep claim: bx = TL / VEC threads share a check (together they move one contiguous
+// TL * w byte row per access), a warp is 32 / bx checks wide and takes rows_per_claim passes per claim.  WARPS
+// claim work, not CTAs: no CTA barrier anywhere after the initial fill, so the warps of an SM drift apart and cover
+// each other's memory round trips.  fp32: 128 registers, two CTAs of 256 threads per SM.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
@@ -15,10 +13,9 @@
 #include <cstdlib>
 #include <type_traits>
 
-// register-lean fused item: row loads issued in batches of FUSED_BATCH_EDGES edges (4 loads each), no index
-// prefetch into registers.  Measured on B200 (2048 frames x 50 iterations, 1024 lanes, 128 registers, 2 CTAs/SM):
-// batches of 3 edges 63.7 ms, 4 edges 59.8 ms, 5 edges 67.3 ms, all 6 at once 64.5 ms (spills); 4 it is.
-#define FUSED_HALF_BATCH 1
+// Row loads of a fused item are issued in batches of FUSED_BATCH_EDGES edges (4 loads each).  Measured on B200
+// (2048 frames x 50 iterations, 1024 lanes, 128 registers, 2 CTAs/SM): batches of 3 edges 63.7 ms, 4 edges 59.8 ms,
+// 5 edges 67.3 ms, all 6 at once 64.5 ms (spills); 4 it is.
 #define FUSED_BATCH_EDGES 4
 #include "qr_decode_fused.cuh"
 #include "qr_handles.h"
@@ -39,250 +36,533 @@ __device__ __forceinline__ uint64_t l2_policy(int kind)
     return p;
 }
 
-// Work distribution: WARPS claim work, not CTAs.  A warp is 32 / bx checks wide (bx = TL / VEC threads share a
-// check) and takes rows_per_claim passes per claim from one global counter, in tile order; the atomic of the
-// NEXT claim is issued before the current one is processed.  No CTA barrier inside the phase, so the warps of
-// an SM drift apart and cover each other's memory round trips (measured: a CTA-wide claim with its barrier cost
-// 2.1 us per claim, profiles/r1_fused_experiments.txt f7/f8).  Per-lane "some check unsatisfied" flags are
-// OR-reduced inside the warp and stored per tile (idempotent stores of 1).
-template <typename T, int VEC, int DSEL>
-__device__ __forceinline__ void fused_phase(const FusedParams<T> &F, int cur, uint64_t pol_ld, uint64_t pol_st)
+__device__ __forceinline__ int32_t ld_volatile(const int32_t *p) { return *reinterpret_cast<const volatile int32_t *>(p); }
+
+// ---------------------------------------------------------------------------------------------
+// BK(tile, round): advance the lane state machine of one tile (decoder.pyx:431-436), one warp, lane i of the warp
+// = lane i (+32, +64 ...) of the tile.  Finished frames get their flags, the lane its next frame; the tile's
+// refill list is written for PP.
+template <typename T>
+__device__ __forceinline__ void tile_bookkeep(const FusedParams<T> &F, int32_t tile, int32_t round)
 {
     const DecodeParams<T> &P = F.P;
-    const int32_t bx = F.tl / VEC;                    // threads per check row (<= 32)
-    const int32_t lane = threadIdx.x & 31;
-    const int32_t tx = lane % bx, tyw = lane / bx, wy = 32 / bx;
-    const int32_t claim_rows = wy * F.rows_per_claim, C = (int32_t)P.C;
-    const int32_t cpt = (C + claim_rows - 1) / claim_rows, total = cpt * F.tiles;
-    int32_t tile_prev = -1;
-    uint32_t bad = 0;
-    LaneInfo<VEC> L;
-    L.active = 0;
-    TileView<T> V;
-    const int32_t minfin = ld_stream(&P.ctrl[CTRL_MINFIN]);   // fixed for the whole phase (updated between phases)
-    auto flush = [&]() {
-        uint32_t b = bad;
-        for (int32_t o = bx; o < 32; o <<= 1) b |= __shfl_xor_sync(0xffffffffu, b, o);
-        if (tyw == 0) {
-#pragma unroll
-            for (int k = 0; k < VEC; ++k)
-                if (b >> k & 1) P.unsat[cur][tile_prev * F.tl + tx * VEC + k] = 1;
+    const int32_t lid = threadIdx.x & 31;
+    const int32_t minfin_used = ld_volatile(&F.tile_minfin[tile]);      // what the sweep just finished went by
+    int32_t listed = 0;
+    int32_t next_iter[kFusedMaxTile / 32], next_fresh[kFusedMaxTile / 32];   // this thread's lanes after the update
+    RefillEntry *list = F.rlist + (int64_t)tile * F.tl;
+    for (int32_t base = 0; base < F.tl; base += 32) {
+        const int32_t lane = tile * F.tl + base + lid;
+        LaneState s = ld_stream(&P.st[0][lane]);
+        const int32_t unsat = ld_stream(&P.unsat[0][lane]);
+        const BkDecision d = bk_decide(s, unsat, P.maxiter);
+        const bool fin = d.fin_ok || d.fin_fail;
+        const uint32_t m_fin = __ballot_sync(0xffffffffu, fin);
+        const int32_t n_fin = __popc(m_fin), rank = __popc(m_fin & ((1u << lid) - 1u));
+        int32_t first_frame = 0;
+        if (n_fin) {
+            if (lid == 0) first_frame = atomicAdd(&P.ctrl[CTRL_NEXT_FRAME], n_fin);
+            first_frame = __shfl_sync(0xffffffffu, first_frame, 0);
         }
-        bad = 0;
-    };
-    // static_share (per mille) of the claims of a step is dealt round-robin to the warps without any atomic
-    // (claims gw, gw + W, ...); the rest is claimed dynamically so that a slow SM does not hold the barrier
-    const int32_t W = (int32_t)(gridDim.x * (kFBlock / 32)), gw = (int32_t)(blockIdx.x * (kFBlock / 32) + (threadIdx.x >> 5));
-    const int32_t n_static = (int32_t)((int64_t)total * F.static_share / 1000) / W * W;
-    int32_t nxt = gw < n_static ? gw : -1;
-    if (nxt < 0) {
-        if (lane == 0) nxt = n_static + atomicAdd(&P.work[0], 1);
-        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+        unsigned long long it_sum = fin ? (unsigned long long)s.iter : 0ULL;
+        for (int o = 16; o > 0; o >>= 1) it_sum += __shfl_xor_sync(0xffffffffu, it_sum, o);
+        if (fin) {
+            P.success[s.frame] = d.fin_ok ? 1 : 0;
+            P.iters[s.frame] = d.fin_ok ? s.iter : P.maxiter;
+            if (d.fin_ok && s.iter > 0) atomicMin(&P.ctrl[CTRL_MINFIN], s.iter);   // (0 iterations = input already consistent: no signal)
+            RefillEntry e;
+            e.lane = base + lid;
+            e.retire = s.frame;
+            const int32_t nf = first_frame + rank;
+            e.frame = (int64_t)nf < P.frames ? nf : -1;
+            e.post_valid = (F.post && stores_post(s.iter, P.maxiter, minfin_used)) ? 1 : 0;
+            list[listed + rank] = e;
+            s.frame = e.frame; s.iter = 0; s.fresh = e.frame >= 0 ? 1 : 0;
+        } else if (s.frame >= 0) {
+            s.iter += 1;
+            s.fresh = 0;
+        }
+        s.retire = -1;
+        P.st[0][lane] = s;
+        P.unsat[0][lane] = 0;
+        next_iter[base / 32] = s.frame >= 0 ? s.iter : -1;
+        next_fresh[base / 32] = s.fresh;
+        if (lid == 0 && n_fin) {
+            atomicAdd(&P.stats[0], it_sum);
+            atomicAdd(&P.ctrl[CTRL_REMAINING], -n_fin);
+        }
+        listed += n_fin;
     }
-    for (;;) {
-        const int32_t cl = nxt;
-        if (cl >= total) break;
-        const bool dyn = cl + W >= n_static;                   // the next claim comes from the counter
-        if (!dyn) nxt = cl + W;
-        else if (lane == 0) nxt = n_static + atomicAdd(&P.work[0], 1);   // in flight while this claim is processed
-        const int32_t tile = cl / cpt;
-        if (tile != tile_prev) {
-            if (tile_prev >= 0) flush();
-            L = load_lane_info<T, VEC>(P, cur, (tile * F.tl) / VEC + tx);
-            mark_post_lanes<T, VEC>(F, L, minfin);
-            V = tile_view(F, cur, tile);
-            tile_prev = tile;
-        }
-        if (L.active) {
-            const int32_t c0 = (cl - tile * cpt) * claim_rows, c1 = min(c0 + claim_rows, C);
-            for (int32_t b = 0; b < P.n_bins; ++b) {
-                const CheckBin bin = P.bins[b];
-                const int32_t lo = max(c0, bin.chk_begin), hi = min(c1, bin.chk_begin + bin.count);
-                if (lo >= hi) continue;
-                const CheckBin sub{bin.degree, lo, hi - lo, bin.slot_begin + (lo - bin.chk_begin) * bin.degree};
-                if constexpr (DSEL > 0) bad |= run_fused_bin<T, VEC, DSEL>(V, F.nbr, L, tx * VEC, sub, tyw, wy, pol_ld, pol_st);
-                else bad |= run_fused_bin_any<T, VEC>(V, F.nbr, L, tx * VEC, sub, tyw, wy, pol_ld, pol_st);
-            }
-        }
-        if (dyn) nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    __syncwarp();
+    // PP of this tile: R items into the ready queue (nothing when no frame finished: the common case below the
+    // waterfall).  Ticket h lives in ring slot h mod size; the sequence number h + 1 in the upper half marks it
+    // published.  At most one PP per tile is outstanding (the tile's next sweep waits for it), so the ring, sized
+    // tiles * R, cannot be lapped.
+    int32_t first_ticket = 0, new_minfin = 0, expect = 0;
+    if (lid == 0) {
+        if (listed) first_ticket = atomicAdd(&P.ctrl[CTRL_PP_RESERVE], F.pp_items);
+        new_minfin = ld_volatile(&P.ctrl[CTRL_MINFIN]);
+        expect = ld_volatile(&F.pp_expect[tile]) + (listed ? F.pp_items : 0);
+        F.rcount[tile] = listed;
+        F.tile_minfin[tile] = new_minfin;                             // fixed for the tile's next sweep
+        F.pp_expect[tile] = expect;
+        if (tile == 0) atomicAdd(&P.stats[1], 1ULL);                  // rounds executed
     }
-    if (tile_prev >= 0) flush();
+    first_ticket = __shfl_sync(0xffffffffu, first_ticket, 0);
+    new_minfin = __shfl_sync(0xffffffffu, new_minfin, 0);
+    expect = __shfl_sync(0xffffffffu, expect, 0);
+    // what the next sweep reads per lane: one byte, bit 0 runs a frame, bit 1 first half-iteration (c2v counts as
+    // zero), bit 2 store the posterior (the lane may finish in that sweep)
+    for (int32_t base = 0; base < F.tl; base += 32) {
+        const int32_t it = next_iter[base / 32];
+        uint8_t fl = 0;
+        if (it >= 0) fl = (uint8_t)(1 | (next_fresh[base / 32] ? 2 : 0) | ((F.post && stores_post(it, P.maxiter, new_minfin)) ? 4 : 0));
+        F.lane_flags[tile * F.tl + base + lid] = fl;
+    }
+    __threadfence();                                                  // release: states, flags, lists, counters
+    __syncwarp();
+    if (listed) {
+        for (int32_t it = lid; it < F.pp_items; it += 32) {
+            const uint32_t h = (uint32_t)(first_ticket + it);
+            const unsigned long long ent = ((unsigned long long)(h + 1u) << 32) |
+                                           (unsigned long long)(((uint32_t)tile << 8) | ((uint32_t)it << 1) | (uint32_t)(round & 1));
+            *reinterpret_cast<volatile unsigned long long *>(&F.ppq[h % (uint32_t)F.ppq_size]) = ent;
+        }
+    }
+    // rounds book-kept (low word) and PP items published so far (high word) in ONE word: a sweep claim reads both
+    // with a single load and compares the second with pp_done
+    if (lid == 0)
+        *reinterpret_cast<volatile unsigned long long *>(&F.bk_word[tile]) =
+            ((unsigned long long)(uint32_t)expect << 32) | (unsigned long long)(uint32_t)(round + 1);
+    __syncwarp();
 }
 
-// REFILL PHASE of the fused schedule.  `buf` = lane-state buffer (and refill list) the bookkeeping of this
-// step wrote; `cur` = message buffer the step READ (finished frames' posteriors are llr + its columns).
-// Work item = (listed lane, block of kFBlock * kFRefillRows rows), all loads of a thread issued before its stores.
-constexpr int kFRefillRows = 4;
+// ---------------------------------------------------------------------------------------------
+// PP item `item` of (tile, round): rows [N item / R, N (item + 1) / R) of the variables and the same share of the
+// checks, for every lane of the tile's refill list.  One warp; lane i takes rows r0 + i, r0 + i + 32, ...; all loads
+// of a batch of kPPRows rows are issued before their stores.  `cur` = message buffer the sweep read.
+constexpr int kPPRows = 4;
 
 template <typename T>
-__device__ __forceinline__ void fused_refill_phase(const FusedParams<T> &F, int buf, int cur)
+__device__ __forceinline__ int32_t tile_pp_item(const FusedParams<T> &F, int32_t tile, int32_t item, int cur)
 {
     const DecodeParams<T> &P = F.P;
-    const int32_t cnt = ld_stream(&P.ctrl[CTRL_REFILL_CNT + buf]);
-    const int32_t span = kFBlock * kFRefillRows;
+    const int32_t cnt = ld_stream(&F.rcount[tile]);     // (stable until this PP is complete: the next BK of the tile comes after it)
+    if (cnt == 0) return 0;
+    const int32_t lid = threadIdx.x & 31, tl = F.tl, R = F.pp_items;
+    const int32_t v0 = (int32_t)(P.N * item / R), v1 = (int32_t)(P.N * (item + 1) / R);
+    const int32_t c0 = (int32_t)(P.C * item / R), c1 = (int32_t)(P.C * (item + 1) / R);
+    const RefillEntry *list = F.rlist + (int64_t)tile * tl;
+    for (int32_t ei = 0; ei < cnt; ++ei) {
+        const RefillEntry e = ld_stream(&list[ei]);
+        T *llr_col = P.llr + (int64_t)tile * P.N * tl + e.lane;
+        // ---- ship the retired frame's posteriors
+        if (e.retire >= 0 && P.post_out) {
+            const bool never_iterated = ld_stream(&P.iters[e.retire]) == 0;
+            if (never_iterated || !e.post_valid) {
+                // rare paths, element by element: the copy / +0.0 semantics of a frame that never iterated, and the
+                // rebuild llr + sum c2v of a frame that converged earlier than anything seen before
+                RefillEntry only = e;
+                only.frame = -1;
+                for (int32_t n = v0 + lid; n < v1; n += 32) fused_pp_var_elem<T>(F, cur, only, tile, n);
+            } else {
+                const T *pc = F.post + (int64_t)tile * P.N * tl + e.lane;
+                for (int32_t n0 = v0 + lid; n0 < v1; n0 += 32 * kPPRows) {
+                    T v[kPPRows];
+#pragma unroll
+                    for (int i = 0; i < kPPRows; ++i) {
+                        const int32_t n = n0 + 32 * i;
+                        if (n < v1) v[i] = ld_stream(&pc[(int64_t)n * tl]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < kPPRows; ++i) {
+                        const int32_t n = n0 + 32 * i;
+                        if (n < v1) store_output_llr(P.post_out, P.post_out_f64, (int64_t)e.retire * P.N + n, (double)v[i]);
+                    }
+                }
+            }
+        }
+        // ---- admit the next frame: channel LLRs and syndrome into the lane's columns
+        if (e.frame >= 0) {
+            for (int32_t n0 = v0 + lid; n0 < v1; n0 += 32 * kPPRows) {
+                T v[kPPRows];
+#pragma unroll
+                for (int i = 0; i < kPPRows; ++i) {
+                    const int32_t n = n0 + 32 * i;
+                    if (n < v1) v[i] = load_input_llr<T>(P.llr_in, P.llr_in_f64, (int64_t)e.frame * P.N + n);
+                }
+#pragma unroll
+                for (int i = 0; i < kPPRows; ++i) {
+                    const int32_t n = n0 + 32 * i;
+                    if (n < v1) llr_col[(int64_t)n * tl] = v[i];
+                }
+            }
+            uint8_t *synd_col = P.synd + (int64_t)tile * P.C * tl + e.lane;
+            for (int32_t k0 = c0 + lid; k0 < c1; k0 += 32 * kPPRows) {
+                uint8_t sy[kPPRows];
+#pragma unroll
+                for (int i = 0; i < kPPRows; ++i) {
+                    const int32_t ci = k0 + 32 * i;
+                    if (ci < c1) sy[i] = P.synd_in[(int64_t)e.frame * P.C + P.chk_order[ci]];
+                }
+#pragma unroll
+                for (int i = 0; i < kPPRows; ++i) {
+                    const int32_t ci = k0 + 32 * i;
+                    if (ci < c1) synd_col[(int64_t)ci * tl] = sy[i];
+                }
+            }
+        }
+    }
+    return cnt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// INITIAL FILL: first generation of frames into the lanes (lane l takes frame l), whole grid, before the stream
+// starts.  Work item = (lane, block of kFBlock * kFillRows rows), row-block-major so that CTAs resident at the same
+// time write the same rows of neighbouring lanes and share the sectors of the lane-interleaved rows through L2.
+constexpr int kFillRows = 4;
+
+template <typename T>
+__device__ __forceinline__ void fused_initial_fill(const FusedParams<T> &F)
+{
+    const DecodeParams<T> &P = F.P;
+    const int32_t cnt = (int32_t)min((int64_t)P.lanes, P.frames);
+    const int32_t span = kFBlock * kFillRows, tl = F.tl;
     const int32_t vitems = (int32_t)((P.N + span - 1) / span), citems = (int32_t)((P.C + span - 1) / span);
     const int64_t total = (int64_t)cnt * (vitems + citems);
-    const int32_t tl = F.tl;
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
-        const int32_t e = (int32_t)(item % cnt), r = (int32_t)(item / cnt);
-        const int32_t lane = ld_stream(&P.refill_list[(int64_t)buf * P.lanes + e]);
-        const LaneState s = ld_stream(&P.st[buf][lane]);
-        const int32_t tile = lane / tl, lt = lane % tl;
+        const int32_t lane = (int32_t)(item % cnt), r = (int32_t)(item / cnt);
+        const int32_t tile = lane / tl, lt = lane % tl, frame = lane;
         if (r >= vitems) {
-            if (s.frame >= 0 && s.fresh) {
-                const int32_t c0 = (r - vitems) * span + threadIdx.x;
-                uint8_t sy[kFRefillRows];
+            const int32_t c0 = (r - vitems) * span + threadIdx.x;
+            uint8_t sy[kFillRows];
 #pragma unroll
-                for (int i = 0; i < kFRefillRows; ++i) {
-                    const int32_t ci = c0 + i * kFBlock;
-                    if (ci < P.C) sy[i] = P.synd_in[(int64_t)s.frame * P.C + P.chk_order[ci]];
-                }
+            for (int i = 0; i < kFillRows; ++i) {
+                const int32_t ci = c0 + i * kFBlock;
+                if (ci < P.C) sy[i] = P.synd_in[(int64_t)frame * P.C + P.chk_order[ci]];
+            }
 #pragma unroll
-                for (int i = 0; i < kFRefillRows; ++i) {
-                    const int32_t ci = c0 + i * kFBlock;
-                    if (ci < P.C) P.synd[((int64_t)tile * P.C + ci) * tl + lt] = sy[i];
-                }
+            for (int i = 0; i < kFillRows; ++i) {
+                const int32_t ci = c0 + i * kFBlock;
+                if (ci < P.C) P.synd[((int64_t)tile * P.C + ci) * tl + lt] = sy[i];
             }
             continue;
         }
         const int32_t n0 = r * span + threadIdx.x;
         T *llr_col = P.llr + (int64_t)tile * P.N * tl + lt;
-        const bool post_valid = F.post && s.retire >= 0 && ld_stream(&F.postok[(int64_t)buf * P.lanes + lane]) != 0;
-        if (s.retire >= 0 && P.post_out && post_valid && ld_stream(&P.iters[s.retire]) != 0) {
-            // the phase stored this frame's posteriors: one column of N elements
-            const T *pc = F.post + (int64_t)tile * P.N * tl + lt;
-            T v[kFRefillRows];
+        T v[kFillRows];
 #pragma unroll
-            for (int i = 0; i < kFRefillRows; ++i) {
-                const int32_t n = n0 + i * kFBlock;
-                if (n < P.N) v[i] = ld_stream(&pc[(int64_t)n * tl]);
-            }
-#pragma unroll
-            for (int i = 0; i < kFRefillRows; ++i) {
-                const int32_t n = n0 + i * kFBlock;
-                if (n < P.N) store_output_llr(P.post_out, P.post_out_f64, (int64_t)s.retire * P.N + n, (double)v[i]);
-            }
-        } else if (s.retire >= 0 && P.post_out) {
-            if (ld_stream(&P.iters[s.retire]) == 0) {
-                LaneState only_retire = s;
-                only_retire.frame = -1;
-                for (int i = 0; i < kFRefillRows; ++i) {
-                    const int32_t n = n0 + i * kFBlock;
-                    if (n < P.N) fused_refill_var_elem<T>(F, cur, only_retire, lane, n);
-                }
-            } else {
-                const T *c = F.c2v[cur] + (int64_t)tile * P.E * tl + lt;
-                int32_t sl[kFRefillRows][3];
-                T v[kFRefillRows][4];
-#pragma unroll
-                for (int i = 0; i < kFRefillRows; ++i) {
-                    const int32_t n = n0 + i * kFBlock;
-                    if (n < P.N) {
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) sl[i][j] = P.var_slot[3 * n + j];
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < kFRefillRows; ++i) {
-                    const int32_t n = n0 + i * kFBlock;
-                    if (n < P.N) {
-                        v[i][0] = ld_stream(&llr_col[(int64_t)n * tl]);
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) v[i][1 + j] = ld_stream(&c[(int64_t)sl[i][j] * tl]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < kFRefillRows; ++i) {
-                    const int32_t n = n0 + i * kFBlock;
-                    if (n < P.N) {
-                        T acc = v[i][0] + v[i][1];     // decoder.pyx:291-293, ascending edge id
-                        acc = acc + v[i][2];
-                        acc = acc + v[i][3];
-                        store_output_llr(P.post_out, P.post_out_f64, (int64_t)s.retire * P.N + n, (double)acc);
-                    }
-                }
-            }
+        for (int i = 0; i < kFillRows; ++i) {
+            const int32_t n = n0 + i * kFBlock;
+            if (n < P.N) v[i] = load_input_llr<T>(P.llr_in, P.llr_in_f64, (int64_t)frame * P.N + n);
         }
-        if (s.frame >= 0 && s.fresh) {
-            T v[kFRefillRows];
 #pragma unroll
-            for (int i = 0; i < kFRefillRows; ++i) {
-                const int32_t n = n0 + i * kFBlock;
-                if (n < P.N) v[i] = load_input_llr<T>(P.llr_in, P.llr_in_f64, (int64_t)s.frame * P.N + n);
-            }
-#pragma unroll
-            for (int i = 0; i < kFRefillRows; ++i) {
-                const int32_t n = n0 + i * kFBlock;
-                if (n < P.N) llr_col[(int64_t)n * tl] = v[i];
-            }
+        for (int i = 0; i < kFillRows; ++i) {
+            const int32_t n = n0 + i * kFBlock;
+            if (n < P.N) llr_col[(int64_t)n * tl] = v[i];
         }
     }
 }
 
-template <typename T, int VEC, int DSEL>
-__global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(FusedParams<T> F)
+// ---------------------------------------------------------------------------------------------
+// One claim of F(tile, round): checks [c0, c1) of the tile for the warp.
+template <typename T, int VEC, int DSEL, int VDEG>
+__device__ __forceinline__ uint32_t fused_claim(const FusedParams<T> &F, const TileView<T> &V, const LaneInfo<VEC> &L,
+                                                int32_t c0, int32_t c1, int32_t tx, int32_t tyw, int32_t wy,
+                                                uint64_t pol_ld, uint64_t pol_st)
 {
-    __shared__ int32_t s_last;
+    const DecodeParams<T> &P = F.P;
+    uint32_t bad = 0;
+    if constexpr (std::is_same<T, float>::value && VEC == 4 && DSEL == 6 && VDEG == 3) {
+        {
+            // (this instantiation is only launched with lean records: the generic item is not compiled into it)
+            // check-regular graph: internal check ci has CSR slots [6 ci, 6 ci + 6)
+            const NbrL *rec = static_cast<const NbrL *>(F.nbr_lean);
+            const int32_t lt4 = tx * VEC * 4;
+            const char *llr_t = reinterpret_cast<const char *>(V.llr) + lt4;
+            const char *cold_t = reinterpret_cast<const char *>(V.c_old) + lt4;
+            char *cnew_t = reinterpret_cast<char *>(V.c_new) + lt4;
+            char *post_t = reinterpret_cast<char *>(V.post) + lt4;
+            const uint8_t *synd_t = V.synd + tx * VEC;
+            for (int32_t ci = c0 + tyw; ci < c1; ci += wy) {
+                if (L.fresh) bad |= fused_item_lean<6, true>(llr_t, cold_t, cnew_t, post_t, synd_t, rec, ci, 6 * ci, V.tl, L.fresh, L.wpost, L.active, pol_ld, pol_st);
+                else bad |= fused_item_lean<6, false>(llr_t, cold_t, cnew_t, post_t, synd_t, rec, ci, 6 * ci, V.tl, 0u, L.wpost, L.active, pol_ld, pol_st);
+            }
+            return bad;
+        }
+    } else
+    for (int32_t b = 0; b < P.n_bins; ++b) {
+        const CheckBin bin = P.bins[b];
+        const int32_t lo = max(c0, bin.chk_begin), hi = min(c1, bin.chk_begin + bin.count);
+        if (lo >= hi) continue;
+        const CheckBin sub{bin.degree, lo, hi - lo, bin.slot_begin + (lo - bin.chk_begin) * bin.degree};
+        if constexpr (DSEL > 0) bad |= run_fused_bin<T, VEC, DSEL, VDEG>(V, F.nbr, L, tx * VEC, sub, tyw, wy, pol_ld, pol_st);
+        else bad |= run_fused_bin_any<T, VEC>(V, F.nbr, L, tx * VEC, sub, tyw, wy, pol_ld, pol_st);
+    }
+    return bad;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Per-warp control block in shared memory.  The sweep item needs every register it can get (16 row loads in
+// flight + 24 message values + the check-node recursion at 128 registers per thread); whatever is only touched
+// BETWEEN items lives here, not in registers.  All lanes read (broadcast), all lanes write the same value.
+struct WarpCtl {
+    unsigned long long nxt;           // next claim id (lane 0's atomic result, broadcast)
+    unsigned long long slot, bk;      // prefetched for the NEXT claim: ticket slot, the tile's {PP published | rounds book-kept}
+    uint32_t ticket;
+    int32_t done, ppd;                // prefetched: CTRL_COMPLETED, the next tile's PP items done
+    int32_t round, tile, chunk;       // current claim
+    int32_t n_round, n_tile, n_chunk; // next claim
+    int32_t sig_tile, sig_round;      // finished claim not yet counted
+    int32_t cnt_tile, cnt_round, cnt_val;   // count issued, result arrives during the next claim
+    uint32_t flags, n_flags;          // lane flag bytes of this thread's lanes: kept per LANE below, not here
+    int32_t n_have_flags;
+};
+
+// (cold paths out of line; F is a __grid_constant__ kernel parameter, so the reference is a pointer into the
+// constant bank -- no per-thread copy of the parameter block is ever made)
+template <typename T>
+__device__ __noinline__ void tile_bookkeep_cold(const FusedParams<T> &F, int32_t tile, int32_t round)
+{
+    tile_bookkeep<T>(F, tile, round);
+}
+template <typename T>
+__device__ __noinline__ int32_t tile_pp_item_cold(const FusedParams<T> &F, int32_t tile, int32_t item, int cur)
+{
+    return tile_pp_item<T>(F, tile, item, cur);
+}
+
+// The kernel.  Two sources of work for a warp:
+//   * the PP ready queue: every warp holds one ticket; when the item behind its ticket has been published (by the BK
+//     of some tile) it is processed before the next sweep claim -- the tile's rows are then still in L2;
+//   * the static stream of sweep claims: claim q of P.work[0], round = q / (T cpt), tile = (q / cpt) mod T,
+//     chunk = q mod cpt (q < 2^32: the host cuts larger batches).
+// Consecutive claims of a warp belong to DIFFERENT tiles (the grid covers about one tile per wave), so everything a
+// claim needs to know about its tile is fetched while the PREVIOUS claim computes, between its passes:
+//   after pass 0:  the count of the claim before is issued (release fence + atomic: who finishes a sweep LAST runs
+//                  BK), the next claim id (atomic issued at the top) is taken, and one batch of loads goes out for
+//                  it: exit flag, this warp's ticket slot, the next tile's {PP items published, rounds book-kept}
+//                  word and its PP-items-done counter;
+//   after pass 1:  if those say the next tile is ready, its lane flag bytes are loaded.
+// A claim therefore starts without a single exposed round trip; only when the next tile is NOT ready (few tiles, or
+// the end of a batch) does the warp fall back to loading and waiting in place.
+template <typename T, int VEC, int DSEL, int VDEG>
+__global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __grid_constant__ FusedParams<T> F)
+{
     const DecodeParams<T> &P = F.P;
     cg::grid_group grid = cg::this_grid();
-    const uint64_t pol_ld = l2_policy(F.hints >= 2 ? 2 : 0), pol_st = l2_policy(F.hints >= 1 ? 1 : 0);
-    fused_refill_phase<T>(F, 0, 0);      // first generation of frames into the lanes
+    fused_initial_fill<T>(F);
     grid.sync();
-    for (int step = 0;; ++step) {
-        const int cur = step & 1;
-        fused_phase<T, VEC, DSEL>(F, cur, pol_ld, pol_st);
-        // the last CTA to get here advances the lane state machine (decoder.pyx:431-436) for every lane
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(&P.ctrl[CTRL_ARRIVE], 1) == (int32_t)gridDim.x - 1;
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            if (threadIdx.x == 0) {
-                P.ctrl[CTRL_ARRIVE] = 0;
-                P.work[0] = 0;
-                P.ctrl[CTRL_REFILL_CNT + (cur ^ 1)] = 0;
-                atomicAdd(&P.stats[1], 1ULL);
-            }
-            __syncthreads();
-            const int32_t minfin = ld_stream(&P.ctrl[CTRL_MINFIN]);    // what the phase of this step went by
-            for (int32_t jv = threadIdx.x; jv < P.lanes / VEC; jv += kFBlock) {
-                LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
-                decide_lanes<T, VEC>(P, cur, L);
-                fused_note_finishers<T, VEC>(F, cur ^ 1, L, minfin);
-                bookkeep_lanes<T, VEC>(P, cur, step, L);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) P.ctrl[CTRL_MINFIN] = *(volatile int32_t *)&P.ctrl[CTRL_MINFIN_NEXT];
+
+    __shared__ WarpCtl s_ctl[kFBlock / 32];
+    volatile WarpCtl &w = s_ctl[threadIdx.x >> 5];
+    const int32_t lid = threadIdx.x & 31;
+    const uint32_t cpt = (uint32_t)(((int32_t)P.C + (32 / (F.tl / VEC)) * F.rows_per_claim - 1) / ((32 / (F.tl / VEC)) * F.rows_per_claim));
+    using Flags = Vec<uint8_t, VEC>;
+
+    auto set_coord = [&](unsigned long long q, bool next) {
+        const uint32_t q32 = (uint32_t)q, per_round = cpt * (uint32_t)F.tiles;
+        const uint32_t round = q32 / per_round, rem = q32 - round * per_round, tile = rem / cpt;
+        if (next) { w.n_round = (int32_t)round; w.n_tile = (int32_t)tile; w.n_chunk = (int32_t)(rem - tile * cpt); }
+        else { w.round = (int32_t)round; w.tile = (int32_t)tile; w.chunk = (int32_t)(rem - tile * cpt); }
+    };
+    // ---- completion counts
+    auto settle_count = [&]() {          // the count issued a claim ago has arrived: the LAST finisher of a sweep runs BK
+        if (w.cnt_tile < 0) return;
+        if ((uint32_t)(w.cnt_val + 1) == cpt * (uint32_t)(w.cnt_round + 1)) {
+            __threadfence();                                       // acquire: every claim of the sweep is visible
+            tile_bookkeep_cold<T>(F, w.cnt_tile, w.cnt_round);
         }
-        grid.sync();
-        if (*(volatile int32_t *)&P.ctrl[CTRL_FIN_STEP] == step) {
-            fused_refill_phase<T>(F, cur ^ 1, cur);
-            grid.sync();
+        w.cnt_tile = -1;
+    };
+    auto issue_count = [&]() {
+        if (w.sig_tile < 0) return;
+        settle_count();
+        __threadfence();                                           // release: messages and flags before the count
+        __syncwarp();
+        int32_t v = 0;
+        if (lid == 0) v = atomicAdd(&F.f_done[w.sig_tile], 1);
+        w.cnt_val = __shfl_sync(0xffffffffu, v, 0);
+        w.cnt_tile = w.sig_tile; w.cnt_round = w.sig_round;
+        w.sig_tile = -1;
+    };
+    // ---- PP service
+    auto take_ticket = [&]() {
+        uint32_t t = 0;
+        if (lid == 0) t = (uint32_t)atomicAdd(&P.ctrl[CTRL_PP_HEAD], 1);
+        w.ticket = __shfl_sync(0xffffffffu, t, 0);
+    };
+    auto serve_pp = [&](unsigned long long slot) -> bool {
+        if ((uint32_t)(slot >> 32) != w.ticket + 1u) return false;
+        __threadfence();                                           // acquire (the publisher released before writing the slot)
+        const uint32_t e = (uint32_t)slot;                         // bits 8.. tile, bits 1..7 item, bit 0 parity of the sweep's round
+        const int32_t tile = (int32_t)(e >> 8);
+        const int32_t cnt = tile_pp_item_cold<T>(F, tile, (int32_t)((e >> 1) & 127u), (int)(e & 1u));
+        __threadfence();                                           // release: shipped posteriors, new columns
+        __syncwarp();
+        if (lid == 0) {
+            const int32_t done = atomicAdd(&F.pp_done[tile], 1) + 1;
+            // every item of this PP complete: its retired frames are fully written out
+            if (done == ld_volatile(&F.pp_expect[tile]) && cnt) atomicAdd(&P.ctrl[CTRL_COMPLETED], cnt);
         }
-        if (*(volatile int32_t *)&P.ctrl[CTRL_REMAINING] <= 0) break;
+        take_ticket();
+        return true;
+    };
+    // ---- what a claim needs to know before it starts (prefetched during the previous claim, or loaded in place)
+    auto load_pre = [&](int32_t tile) {
+        const int32_t done = ld_volatile(&P.ctrl[CTRL_COMPLETED]);
+        const unsigned long long slot = *reinterpret_cast<const volatile unsigned long long *>(&F.ppq[w.ticket % (uint32_t)F.ppq_size]);
+        const unsigned long long bk = ld_acquire_u64(&F.bk_word[tile]);
+        const int32_t ppd = ld_volatile(&F.pp_done[tile]);
+        w.done = done; w.slot = slot; w.bk = bk; w.ppd = ppd;
+    };
+    auto tile_ready = [&](int32_t round) {
+        const unsigned long long bk = w.bk;
+        return round == 0 || ((int32_t)(uint32_t)bk >= round && w.ppd >= (int32_t)(bk >> 32));
+    };
+    auto load_flags = [&](int32_t tile) {
+        const uint8_t *p = F.lane_flags + tile * F.tl + (lid % (F.tl / VEC)) * VEC;
+        if constexpr (VEC == 4) return (uint32_t)__ldcg(reinterpret_cast<const unsigned int *>(p));
+        else return (uint32_t)__ldcg(reinterpret_cast<const unsigned short *>(p));
+    };
+
+    {
+        unsigned long long q = 0;
+        if (lid == 0) q = atomicAdd(reinterpret_cast<unsigned long long *>(P.work), 1ULL);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        set_coord(q, false);
+        take_ticket();
+        w.sig_tile = -1; w.cnt_tile = -1;
+        load_pre(w.tile);
+    }
+    const int32_t frames = (int32_t)P.frames;
+    bool have_flags = false;
+    uint32_t flags = 0, n_flags = 0;          // (per lane: the flag bytes of this thread's VEC lanes)
+    for (;;) {
+        // ---- A. exit, PP service, readiness of the claim's tile
+        if (w.done >= frames) break;
+        if (serve_pp(w.slot)) { load_pre(w.tile); have_flags = false; continue; }
+        if (!tile_ready(w.round)) {
+            // not ready: few tiles, or the tail of a batch.  Count what is pending (it may be what the tile waits
+            // for), then poll, serving the PP queue meanwhile
+            issue_count();
+            settle_count();
+            bool gone = false;
+            for (;;) {
+                load_pre(w.tile);
+                if (w.done >= frames) { gone = true; break; }
+                if (tile_ready(w.round)) break;
+                if (!serve_pp(w.slot)) __nanosleep(100);
+            }
+            if (gone) break;
+            have_flags = false;
+            continue;                                              // (re-check the slot with the fresh loads)
+        }
+        if (!have_flags) flags = load_flags(w.tile);
+        unsigned long long nq = 0;
+        if (lid == 0) nq = atomicAdd(reinterpret_cast<unsigned long long *>(P.work), 1ULL);   // in flight during pass 0
+        // ---- B. the claim
+        uint32_t bad = 0;
+        {
+            const int32_t bx = F.tl / VEC, tx = lid % bx, tyw = lid / bx, wy = 32 / bx;
+            const int32_t tile = w.tile, round = w.round;
+            LaneInfo<VEC> L;
+            L.l0 = tile * F.tl + tx * VEC;
+            L.active = L.fresh = L.wpost = L.fin_ok = L.fin_fail = L.upd = 0;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const uint32_t f = flags >> (8 * k);
+                L.active |= (f & 1u) << k;
+                L.fresh |= ((f >> 1) & 1u) << k;
+                L.wpost |= ((f >> 2) & 1u) << k;
+            }
+            const TileView<T> V = tile_view(F, round & 1, tile);
+            const uint64_t pol_ld = l2_policy(F.hints >= 2 ? 2 : 0), pol_st = l2_policy(F.hints >= 1 ? 1 : 0);
+            const int32_t claim_rows = wy * F.rows_per_claim, C = (int32_t)P.C;
+            const int32_t c0 = w.chunk * claim_rows, c1 = min(c0 + claim_rows, C);
+            const int32_t passes = F.rows_per_claim;
+            for (int32_t r = 0; r < max(passes, 2); ++r) {
+                if (r < passes && L.active) {
+                    const int32_t lo = c0 + r * wy, hi = min(lo + wy, c1);
+                    if (lo < hi) bad |= fused_claim<T, VEC, DSEL, VDEG>(F, V, L, lo, hi, tx, tyw, wy, pol_ld, pol_st);
+                }
+                if (r == 0) {
+                    issue_count();                                     // the claim before this one
+                    nq = __shfl_sync(0xffffffffu, nq, 0);
+                    set_coord(nq, true);
+                    load_pre(w.n_tile);                                // consumed after the next pass
+                    w.n_have_flags = 0;
+                } else if (r == 1) {
+                    if (w.done < frames && (uint32_t)(w.slot >> 32) != w.ticket + 1u && tile_ready(w.n_round)) {
+                        n_flags = load_flags(w.n_tile);
+                        w.n_have_flags = 1;
+                    }
+                }
+            }
+            // per-lane "some check unsatisfied" flags: OR over the warp's check rows, idempotent stores of 1
+            for (int32_t o = bx; o < 32; o <<= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+            if (tyw == 0) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    if (bad >> k & 1) P.unsat[0][tile * F.tl + tx * VEC + k] = 1;
+            }
+            w.sig_tile = tile; w.sig_round = round;                    // counted after pass 0 of the next claim
+        }
+        w.round = w.n_round; w.tile = w.n_tile; w.chunk = w.n_chunk;
+        have_flags = w.n_have_flags != 0; flags = n_flags;
     }
 }
 
-template <typename T, int VEC, int DSEL>
+template <typename T, int VEC, int DSEL, int VDEG>
 static int launch_fused(qr_decoder *d, const FusedParams<T> &F, cudaStream_t stream)
 {
-    const size_t smem = 0;
-    auto kern = k_fused<T, VEC, DSEL>;
+    auto kern = k_fused<T, VEC, DSEL, VDEG>;
     int per_sm = 0;
-    QR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFBlock, smem));
+    QR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFBlock, 0));
     if (per_sm < 1) return fail(QR_ERR_CUDA, "fused decoder kernel does not fit on an SM");
     const int grid = per_sm * d->sm_count;
     d->coop_grid = grid;
     FusedParams<T> Fc = F;
     void *args[] = {&Fc};
-    QR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kFBlock), args, smem, stream));
+    QR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kFBlock), args, 0, stream));
     return QR_OK;
 }
 
 bool fused_eligible(const qr_graph *g)
 {
-    return g->d_slot_nbr != nullptr && g->max_cdeg <= kFusedMaxCheckDegree;
+    return !g->slot_nbr.empty() && g->max_cdeg <= kFusedMaxCheckDegree;
+}
+
+// QR_SCHED_AUTO: the fused schedule pays off when a lane tile's live set (messages read + LLRs) stays in L2 between
+// its d_v re-reads; beyond that it moves MORE bytes than the two-phase schedule (measured)
+bool fused_preferred(const qr_graph *g, size_t w)
+{
+    if (!fused_eligible(g)) return false;
+    const size_t tile_bytes = (size_t)(g->E + g->N) * 32 * w;
+    return tile_bytes <= ((size_t)72 << 20);
+}
+
+__global__ void k_build_lean(const Nbr4 *nbr, int64_t E, int32_t tl, NbrL *out)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < E) out[s] = make_lean_record(nbr[s], tl);
+}
+
+__global__ void k_init_fused(int32_t *ctl, int32_t n_ctl, int32_t *tile_minfin, int32_t tiles, int32_t *ctrl,
+                             uint8_t *lane_flags, int32_t lanes, int64_t frames, int wpost0)
+{
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_ctl) ctl[i] = 0;
+    if (i < tiles) tile_minfin[i] = 0x7fffffff;
+    // first generation: lane l runs frame l, first half-iteration; its posterior is stored only if 0 iterations are allowed
+    if (i < lanes) lane_flags[i] = (int64_t)i < frames ? (uint8_t)(1 | 2 | (wpost0 ? 4 : 0)) : (uint8_t)0;
+    if (i == 0) { ctrl[CTRL_MINFIN] = 0x7fffffff; ctrl[CTRL_COMPLETED] = 0; ctrl[CTRL_PP_HEAD] = 0; ctrl[CTRL_PP_RESERVE] = 0; }
 }
 
 template <typename T, int VEC>
@@ -290,11 +570,23 @@ static int run_batch_fused_v(qr_decoder *d, const DecodeParams<T> &P, cudaStream
 {
     const qr_graph *g = d->g;
     if (!fused_eligible(g))
-        return fail(QR_ERR_INVALID, "fused schedule needs every variable of degree 3 and check degrees <= 8");
+        return fail(QR_ERR_INVALID, "fused schedule needs check degrees <= 8 (and fewer than 2^27 variables)");
     const size_t w = sizeof(T);
     if (!d->c2v2) {
         QR_CUDA_CHECK(cudaMalloc(&d->c2v2, (size_t)g->E * (size_t)d->lanes * w));
         QR_CUDA_CHECK(cudaMemset(d->c2v2, 0, (size_t)g->E * (size_t)d->lanes * w));
+    }
+    int32_t tl = d->fused_tile > 0 ? d->fused_tile : 32;
+    tl = std::min<int32_t>(tl, kFusedMaxTile);
+    while (tl > 32 && (P.lanes % tl || (tl / VEC) > 32)) tl /= 2;   // a check row is shared by at most one warp
+    const int32_t tiles = P.lanes / tl, tiles_max = d->lanes / 32;
+    constexpr int32_t kMaxPPItems = 64;
+    if (!d->fused_ctl) {
+        // per tile: f_done, pp_done, pp_expect, rcount, tile_minfin, bk_word (2 words); the per-lane flag bytes; the
+        // refill lists; the PP ready queue
+        QR_CUDA_CHECK(cudaMalloc((void **)&d->fused_ctl, (size_t)8 * tiles_max * sizeof(int32_t) + (size_t)d->lanes));
+        QR_CUDA_CHECK(cudaMalloc((void **)&d->fused_rlist, (size_t)d->lanes * sizeof(RefillEntry)));
+        QR_CUDA_CHECK(cudaMalloc((void **)&d->fused_ppq, (size_t)tiles_max * kMaxPPItems * sizeof(unsigned long long)));
     }
     FusedParams<T> F;
     F.P = P;
@@ -302,18 +594,46 @@ static int run_batch_fused_v(qr_decoder *d, const DecodeParams<T> &P, cudaStream
     F.c2v[0] = static_cast<T *>(d->c2v);
     F.c2v[1] = static_cast<T *>(d->c2v2);
     F.post = d->fused_store_post ? static_cast<T *>(d->post) : nullptr;
-    F.postok = d->postok;
-    int32_t tl = d->fused_tile > 0 ? d->fused_tile : 32;
-    tl = std::min<int32_t>(tl, kFusedMaxTile);
-    while (tl > 32 && (P.lanes % tl || (tl / VEC) > 32)) tl /= 2;   // a check row is shared by at most one warp
+    F.nbr_lean = nullptr;
+    if (std::is_same<T, float>::value && d->regular_degree == 6 && g->var_deg == 3 && d->fused_lean &&
+        (size_t)(g->E + g->N) * tl * 4 < ((size_t)1 << 32)) {
+        if (!d->fused_nbrl || d->fused_nbrl_tl != tl) {
+            if (!d->fused_nbrl) QR_CUDA_CHECK(cudaMalloc(&d->fused_nbrl, (size_t)g->E * sizeof(NbrL)));
+            k_build_lean<<<(unsigned)((g->E + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const Nbr4 *>(g->d_slot_nbr), g->E, tl,
+                                                                          static_cast<NbrL *>(d->fused_nbrl));
+            QR_CUDA_CHECK(cudaGetLastError());
+            d->fused_nbrl_tl = tl;
+        }
+        F.nbr_lean = d->fused_nbrl;
+    }
     F.tl = tl;
-    F.tiles = P.lanes / tl;
+    F.tiles = tiles;
     F.hints = d->fused_hints;
-    F.prefetch = d->fused_prefetch;
     F.rows_per_claim = d->fused_rpc > 0 ? d->fused_rpc : 4;
-    F.static_share = d->fused_static;
-    if (d->regular_degree == 6) return launch_fused<T, VEC, 6>(d, F, stream);
-    return launch_fused<T, VEC, 0>(d, F, stream);
+    F.dbg = getenv("QAMRECON_FUSED_DBG") ? atoi(getenv("QAMRECON_FUSED_DBG")) : 0;
+    F.pp_items = d->fused_pp_items > 0 ? std::min(d->fused_pp_items, kMaxPPItems)
+                                       : (int32_t)std::min<int64_t>(kMaxPPItems, std::max<int64_t>(4, g->N / 1024));
+    F.f_done = d->fused_ctl;
+    F.pp_done = d->fused_ctl + tiles_max;
+    F.pp_expect = d->fused_ctl + 2 * tiles_max;
+    F.rcount = d->fused_ctl + 3 * tiles_max;
+    F.bk_word = reinterpret_cast<unsigned long long *>(d->fused_ctl + 4 * tiles_max);
+    F.tile_minfin = d->fused_ctl + 6 * tiles_max;
+    F.lane_flags = reinterpret_cast<uint8_t *>(d->fused_ctl + 8 * tiles_max);
+    F.rlist = static_cast<RefillEntry *>(d->fused_rlist);
+    F.ppq = static_cast<unsigned long long *>(d->fused_ppq);
+    F.ppq_size = tiles_max * kMaxPPItems;
+    QR_CUDA_CHECK(cudaMemsetAsync(d->fused_ppq, 0, (size_t)F.ppq_size * sizeof(unsigned long long), stream));
+    k_init_fused<<<(std::max<int32_t>(6 * tiles_max, P.lanes) + 255) / 256, 256, 0, stream>>>(
+        d->fused_ctl, 6 * tiles_max, F.tile_minfin, tiles_max, P.ctrl, F.lane_flags, P.lanes, P.frames,
+        (F.post && P.maxiter == 0) ? 1 : 0);
+    QR_CUDA_CHECK(cudaGetLastError());
+    // <.., 6, 3>: check-regular degree 6, every variable of degree 3 (config 2); in float it runs the lean item and
+    // needs the lean records, otherwise the float kernel for any variable degree takes over
+    const bool reg3 = g->var_deg == 3 && (!std::is_same<T, float>::value || F.nbr_lean != nullptr);
+    if (d->regular_degree == 6 && reg3) return launch_fused<T, VEC, 6, 3>(d, F, stream);
+    if (d->regular_degree == 6) return launch_fused<T, VEC, 6, 0>(d, F, stream);
+    return launch_fused<T, VEC, 0, 0>(d, F, stream);
 }
 
 template <typename T>

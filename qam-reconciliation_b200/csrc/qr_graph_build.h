@@ -103,19 +103,28 @@ inline int build_host_tables(qr_graph &g, const int64_t *vid, const int64_t *cid
                          [&](int32_t a, int32_t b) { return vdeg[a] < vdeg[b]; });
     }
     // neighbour table of the fused schedule: what a check needs to rebuild post[v] = llr[v] + sum c2v
-    // (decoder.pyx:291-293) of each of its variables without a stored posterior
+    // (decoder.pyx:291-293) of each of its variables without a stored posterior (record layout: Nbr4,
+    // qr_decode_fused.cuh)
     g.slot_nbr.clear();
-    if (g.var_deg == 3 && N < (int64_t(1) << 28)) {
-        g.slot_nbr.assign(4 * (size_t)E, 0);
+    // (every variable needs an edge: the posterior of a lane about to finish is stored by the check holding the
+    // variable's first edge)
+    if (N < (int64_t(1) << 27) && g.max_vdeg <= 64 && g.decodable && *std::min_element(vdeg.begin(), vdeg.end()) >= 1) {
+        g.slot_nbr.assign(4 * (size_t)E, -1);
         for (int64_t s = 0; s < E; ++s) {
             const int32_t v = g.slot_var[s];
+            const int32_t q0 = g.var_ptr[v], dv = g.var_ptr[v + 1] - q0;
             int32_t own = -1;
-            for (int j = 0; j < 3; ++j) {
-                const int32_t t = g.var_slot[g.var_ptr[v] + j];
-                g.slot_nbr[4 * s + 1 + j] = t;
-                if (t == s) own = j;
+            for (int j = 0; j < dv; ++j)
+                if (g.var_slot[q0 + j] == s) own = j;
+            if (dv <= 3) {
+                for (int j = 0; j < dv; ++j) g.slot_nbr[4 * s + 1 + j] = g.var_slot[q0 + j];
+                g.slot_nbr[4 * s] = (int32_t)((uint32_t)v | ((uint32_t)own << 28) | ((uint32_t)dv << 30));
+            } else {
+                g.slot_nbr[4 * s] = v | 0x08000000;
+                g.slot_nbr[4 * s + 1] = q0;
+                g.slot_nbr[4 * s + 2] = dv;
+                g.slot_nbr[4 * s + 3] = own;
             }
-            g.slot_nbr[4 * s] = v | (own << 28);
         }
     }
     return QR_OK;

@@ -34,12 +34,15 @@ struct qr_decoder {
     void *c2v = nullptr, *post = nullptr, *llr = nullptr;
     void *c2v2 = nullptr;    // second message buffer of QR_SCHED_FUSED (allocated on first use)
     int fused_tile = 32;     // lanes per L2 tile of the fused schedule (32, 64 or 128)
-    int fused_pipe = 0;      // staging experiments (only with -DQR_FUSED_EXPERIMENTS): 1/2 cp.async stages, 3 TMA bulk rows
-    int fused_prefetch = 0;  // 1: sequential L2 prefetch of the next tile (measured slower on B200)
     int fused_store_post = 1;   // store posteriors of lanes that may finish (cheap shipping), 0: always rebuild them
-    int32_t *postok = nullptr;  // [2][lanes]
-    int fused_static = 0;    // per mille of the claims dealt statically
-    int fused_rpc = 4;       // checks per thread and claim of the register-staged fused phase
+    int fused_rpc = 4;       // checks per thread and claim of a fused sweep
+    int fused_pp_items = 0;  // items per tile post-processing (0: from the code length)
+    int32_t *fused_ctl = nullptr;    // per-tile counters of the tile pipeline
+    void *fused_rlist = nullptr;     // per-tile refill lists
+    void *fused_ppq = nullptr;       // ready queue of post-processing items
+    void *fused_nbrl = nullptr;      // lean neighbour records of the float mode (built for fused_nbrl_tl lanes per tile)
+    int fused_nbrl_tl = 0;
+    int fused_lean = 1;              // 0: the generic item in float mode too (QAMRECON_FUSED_LEAN)
     int fused_hints = 1;     // L2 policy of the fused schedule: 0 none, 1 stores evict-first, 2 + loads evict-last
     uint8_t *synd = nullptr;
     qr::LaneState *st = nullptr;          // [2][lanes]

@@ -444,6 +444,37 @@ QR_HD double g_inv_fast(const double *a, const double *p, const double *thr, con
 // Hermite table (one Newton step on the cubic: |dy| ~ 1e-11, no snap), exponentials are a double range
 // reduction + ONE MUFU.EX2, reciprocals a float seed + one Newton step, the final log a MUFU.LG2 on the
 // mantissa.  Relative error of the LLR ~1e-6 (tests: 1e-5 relative + 1e-6 absolute against the exact replay).
+QR_HD float ex2_f32(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return exp2f(x);
+#endif
+}
+QR_HD float rcp_f32(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+// 2^e as a double, |e| <= 1022 (exact: written into the exponent field)
+QR_HD double pow2_int(int32_t e)
+{
+    e = e < -1022 ? -1022 : (e > 1023 ? 1023 : e);
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)(e + 1023) << 52);
+#else
+    return ldexp(1.0, e);
+#endif
+}
+
 QR_HD double rcp_f32grade(double x)
 {
     if (!(fabs(x) > 1e-30 && fabs(x) < 1e30)) return 1.0 / x;     // outside the float range (rare): the real division
@@ -521,14 +552,16 @@ QR_HD double g_inv_f32grade(const double *a, const double *p, const double *thr,
         const double F0 = tab.F[lo], F1 = tab.F[hi], d0 = tab.f[lo], d1 = tab.f[hi];
         const double dF = F1 - F0, d = target - F0;
         if (dF > 1e-30 && (d0 < d1 ? d0 : d1) > 1e-6) {
-            const double A = tab.h * d0, B = tab.h * d1;
-            const double c2 = 3 * dF - 2 * A - B, c3 = A + B - 2 * dF;     // cubic Hermite through (F, f) at both ends
-            double sx = d * rcp_f32grade(dF);
-            const double G = sx * (A + sx * (c2 + sx * c3));
-            const double Gp = A + sx * (2 * c2 + 3 * sx * c3);
-            sx -= (G - d) * rcp_f32grade(Gp);
-            sx = sx < 0 ? 0 : (sx > 1 ? 1 : sx);
-            return tab.y0 + (lo + sx) * tab.h;
+            // the two differences above are the cancellations that need double; the cubic itself is solved in float
+            const float hf = (float)tab.h, dFf = (float)dF, df = (float)d;
+            const float A = hf * (float)d0, B = hf * (float)d1;
+            const float c2 = 3.0f * dFf - 2.0f * A - B, c3 = A + B - 2.0f * dFf;     // cubic Hermite through (F, f) at both ends
+            float sx = df * rcp_f32(dFf);
+            const float G = sx * fmaf(sx, fmaf(sx, c3, c2), A);
+            const float Gp = fmaf(sx, fmaf(3.0f * sx, c3, 2.0f * c2), A);
+            sx -= (G - df) * rcp_f32(Gp);
+            sx = fminf(fmaxf(sx, 0.0f), 1.0f);
+            return fma((double)sx, tab.h, fma((double)lo, tab.h, tab.y0));
         }
     }
     return g_inv_slow_path(a, p, thr, FYt, order, sigma, s2, target, region, tab);
@@ -572,6 +605,9 @@ struct TablesRef {
     const double *a, *p, *thr, *FYt, *delta;
     const uint8_t *sign;
     const double *ghi = nullptr, *glo = nullptr, *pz = nullptr;   // see SharedTables (fast demapper only)
+    // fp32-grade demapper: (m step)^2 c log2(e) for c = 1 / 2 sigma^2 (g2hi) and c = 1 (g2lo, the reference's
+    // undivided k < j exponent), and the zero-padded probabilities, as floats
+    const float *g2hi = nullptr, *g2lo = nullptr, *pzf = nullptr;
 };
 
 // demap_lappr (noisemapper.pyx:450-540) for ONE symbol: Bob's metric n_hat, Alice's symbol j -> bps
@@ -670,8 +706,16 @@ static QR_HD_NOINLINE double demap_sum_direct(const TablesRef &s, int order, int
     return sum;
 }
 
-// demap_lappr for ONE symbol at fp32 grade, alphabet size known at compile time (everything unrolled, N / D in
-// registers): equally spaced constellations only (PAMAlphabet always is).  Same formulas as demap_symbol's fast path.
+// demap_lappr for ONE symbol at fp32 grade, alphabet size known at compile time (everything unrolled, accumulators
+// in registers): equally spaced constellations only (PAMAlphabet always is).  Same formulas as demap_symbol's fast
+// path, evaluated in FLOAT after the two cancellations that need double (target - F0 on the table, y_hat - a_j):
+//   * root: linear guess + one Newton step on the Hermite cubic, in float (error ~1e-7 of a 1.5e-3 wide cell);
+//   * the sum over Alice's symbols: term k has the exponent m u - (m step)^2 c, m = k - j, u = 2 (y_hat - a_j) step c;
+//     all exponents of a hypothesis are formed in log2 units, their integer maximum e_max is factored out (the
+//     undivided k < j exponents of the reference reach several hundred for 8-PAM: 2^e_max is applied to the weight
+//     as an exact exponent-field operation on a double), each term is one FADD + MUFU.EX2 + FFMA;
+//   * weights delta_i / sum accumulate in double (their range spans hundreds of binades), the LLR is one
+//     MUFU.LG2 on the mantissa of N / D.
 template <int BPS>
 QR_HD void demap_symbol_f32grade(const MapperView &m, const TablesRef &s, double nv, int32_t j, bool corrected,
                                  double alpha, double *out)
@@ -680,9 +724,12 @@ QR_HD void demap_symbol_f32grade(const MapperView &m, const TablesRef &s, double
     const double inv_two_s2 = rcp_f32grade(2 * m.noise_var);
     const double step = M > 1 ? s.a[1] - s.a[0] : 0.0;
     const InvTable tab{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h, m.inv_jump, m.inv_jn};
-    const double *glo = corrected ? s.ghi : s.glo;
-    const double *pj = s.pz + (M - 1) + j;
-    const double aj = s.a[j], pjj = s.p[j];
+    const float *g2lo = corrected ? s.g2hi : s.g2lo;
+    const float *pj = s.pzf + (M - 1) + j;
+    const double aj = s.a[j];
+    const double k_hi = 2.0 * step * inv_two_s2 * 1.4426950408889634;                       // u (log2 units) per unit of y_hat - a_j
+    const double k_lo = -2.0 * step * (corrected ? inv_two_s2 : 1.0) * 1.4426950408889634;
+    const float pjj = pj[0];
     double N[BPS], D[BPS];
 #pragma unroll
     for (int k = 0; k < BPS; ++k) { N[k] = 0; D[k] = 0; }
@@ -691,21 +738,32 @@ QR_HD void demap_symbol_f32grade(const MapperView &m, const TablesRef &s, double
         const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
         const double yh = g_inv_f32grade(s.a, s.p, s.thr, s.FYt, M, m.sigma, m.s2, target, i, tab);
         const double dd = yh - aj;
-        const double u_hi = 2 * dd * step * inv_two_s2, u_lo = -2 * dd * step * (corrected ? inv_two_s2 : 1.0);
-        double sum;
-        if (fabs(u_hi) * (M - 1) < 600.0 && fabs(u_lo) * (M - 1) < 600.0) {
-            const double Eh = exp_f32grade(u_hi), El = exp_f32grade(u_lo);
-            double ph = 1.0, pl = 1.0;
-            sum = pjj;
+        const float uh = (float)(dd * k_hi), ul = (float)(dd * k_lo);
+        double w;
+        if (fabsf(uh) < 300.0f && fabsf(ul) < 300.0f) {
+            float th[M], tlo[M];
+            float tmax = 0.0f;                                   // (the k = j term has exponent 0)
 #pragma unroll
             for (int mm = 1; mm < M; ++mm) {
-                ph *= Eh; pl *= El;
-                sum += pj[mm] * (ph * s.ghi[mm]) + pj[-mm] * (pl * glo[mm]);
+                th[mm] = fmaf((float)mm, uh, -s.g2hi[mm]);
+                tlo[mm] = fmaf((float)mm, ul, -g2lo[mm]);
+                // (terms outside the alphabet carry probability 0: keep them out of the maximum)
+                if (pj[mm] > 0.0f) tmax = fmaxf(tmax, th[mm]);
+                if (pj[-mm] > 0.0f) tmax = fmaxf(tmax, tlo[mm]);
             }
+            const float emax = ceilf(tmax);
+            float sum = pjj * ex2_f32(-emax);
+#pragma unroll
+            for (int mm = 1; mm < M; ++mm) {
+                // (min: a zero-probability term may lie above the maximum; 0 * inf must not happen)
+                sum = fmaf(pj[mm], ex2_f32(fminf(th[mm] - emax, 0.0f)), sum);
+                sum = fmaf(pj[-mm], ex2_f32(fminf(tlo[mm] - emax, 0.0f)), sum);
+            }
+            w = s.delta[i] * (double)rcp_f32(sum) * pow2_int(-(int32_t)emax);      // delta_i / (sum 2^emax)
         } else {
-            sum = demap_sum_direct(s, M, j, yh, corrected, inv_two_s2);
+            // a reconstructed sample absurdly far out (saturated metric): the reference's double arithmetic, out of line
+            w = s.delta[i] / demap_sum_direct(s, M, j, yh, corrected, inv_two_s2);
         }
-        const double w = s.delta[i] * rcp_f32grade(sum);
 #pragma unroll
         for (int k = 0; k < BPS; ++k) {
             const int q = i >> k;

@@ -114,7 +114,10 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
     return 0;
 }
 
-// QR_SCHED_FUSED: one fused phase per step over tile-major arrays, bookkeeping, refill
+// QR_SCHED_FUSED as a tile pipeline (qr_decode_fused.cuh): the stream of work items executed one after the other in
+// stream order -- sweep F(t), bookkeeping BK(t) (what the last finisher of the sweep does on the device), and the
+// post-processing PP one tile behind.  Run sequentially, every wait of the device code is trivially satisfied; what
+// is checked here is the lane state machine, the refill lists, the record decoding and the arithmetic.
 template <typename T, int VEC>
 static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *llr, int llr_dtype,
                               const uint8_t *synd, int64_t frames, int maxiter, uint8_t *success, int32_t *iters,
@@ -123,8 +126,8 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     if (g.slot_nbr.empty() || g.max_cdeg > kFusedMaxCheckDegree || lanes % tl) return -2;
     std::vector<T> c2v0((size_t)g.E * lanes, (T)1e30), c2v1((size_t)g.E * lanes, (T)-3e30), llrw((size_t)g.N * lanes, (T)3e29);
     std::vector<uint8_t> syndw((size_t)g.C * lanes, 0xff);
-    std::vector<LaneState> st(2 * lanes);
-    std::vector<int32_t> unsat(2 * lanes, 0), ctrl(CTRL_WORDS, 0);
+    std::vector<LaneState> st(lanes);
+    std::vector<int32_t> unsat(lanes, 0), ctrl(CTRL_WORDS, 0);
     unsigned long long stats[2] = {0, 0};
     FusedParams<T> F;
     DecodeParams<T> &P = F.P;
@@ -134,69 +137,104 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     P.var_work = g.var_work.empty() ? nullptr : g.var_work.data();
     P.N = g.N; P.C = g.C; P.E = g.E; P.lanes = lanes; P.var_deg = g.var_deg;
     P.c2v = nullptr; P.post = nullptr; P.llr = llrw.data(); P.synd = syndw.data();
-    P.st[0] = st.data(); P.st[1] = st.data() + lanes;
-    P.unsat[0] = unsat.data(); P.unsat[1] = unsat.data() + lanes;
+    P.st[0] = st.data(); P.st[1] = nullptr;
+    P.unsat[0] = unsat.data(); P.unsat[1] = nullptr;
     P.llr_in = llr; P.llr_in_f64 = llr_dtype == QR_F64; P.synd_in = synd;
     P.frames = frames; P.maxiter = maxiter; P.success = success; P.iters = iters;
     P.post_out = post; P.post_out_f64 = post_dtype == QR_F64;
     P.ctrl = ctrl.data(); P.stats = stats; P.work = nullptr; P.refill_list = nullptr;
     F.nbr = reinterpret_cast<const Nbr4 *>(g.slot_nbr.data());
     F.c2v[0] = c2v0.data(); F.c2v[1] = c2v1.data();
-    F.tl = tl; F.tiles = lanes / tl; F.hints = 0; F.prefetch = 0; F.rows_per_claim = 2; F.static_share = 0;
+    const int tiles = lanes / tl;
+    F.tl = tl; F.tiles = tiles; F.hints = 0; F.rows_per_claim = 2; F.pp_items = 3; F.dbg = 0;
     std::vector<T> postw((size_t)g.N * lanes, (T)-7e29);
-    std::vector<int32_t> postok(2 * lanes, 0);
-    F.post = store_post ? postw.data() : nullptr; F.postok = postok.data();
+    F.post = store_post ? postw.data() : nullptr;
+    std::vector<int32_t> tile_minfin(tiles, 0x7fffffff), rcount(tiles, 0);
+    std::vector<RefillEntry> rlist(lanes);
+    F.tile_minfin = tile_minfin.data(); F.rcount = rcount.data(); F.rlist = rlist.data();
+    F.f_done = F.pp_done = F.pp_expect = nullptr; F.bk_word = nullptr; F.lane_flags = nullptr; F.ppq = nullptr; F.ppq_size = 0;
+    // initial fill: lane l takes frame l
     for (int l = 0; l < lanes; ++l) {
         LaneState s;
         s.frame = l < frames ? l : -1; s.iter = 0; s.fresh = s.frame >= 0; s.retire = -1;
-        st[l] = s; st[lanes + l] = s;
+        st[l] = s;
+        if (s.frame < 0) continue;
+        const RefillEntry e{l % tl, -1, s.frame, 0};
+        for (int32_t n = 0; n < g.N; ++n) fused_pp_var_elem<T>(F, 0, e, l / tl, n);
+        for (int32_t ci = 0; ci < g.C; ++ci) fused_pp_chk_elem<T>(F, e, l / tl, ci);
     }
     ctrl[CTRL_NEXT_FRAME] = (int32_t)std::min<int64_t>(lanes, frames);
     ctrl[CTRL_REMAINING] = (int32_t)frames;
-    ctrl[CTRL_FIN_STEP] = -1;
-    ctrl[CTRL_MINFIN] = ctrl[CTRL_MINFIN_NEXT] = 0x7fffffff;
-    int64_t shipped_from_post = 0;
-    auto refill = [&](int buf, int cur) {
-        for (int lane = 0; lane < lanes; ++lane) {
-            const LaneState s = P.st[buf][lane];
-            if (!lane_needs_refill(s)) continue;
-            const bool pv = F.post && s.retire >= 0 && F.postok[(size_t)buf * lanes + lane] != 0;
-            if (pv && P.iters[s.retire] != 0) ++shipped_from_post;
-            for (int32_t n = 0; n < g.N; ++n) fused_refill_var_elem<T>(F, cur, s, lane, n, pv);
-            for (int32_t ci = 0; ci < g.C; ++ci) fused_refill_chk_elem<T>(F, s, lane, ci);
+    ctrl[CTRL_MINFIN] = 0x7fffffff;
+    int64_t shipped_from_post = 0, completed = 0;
+    auto sweep = [&](int tile, int cur) {
+        const TileView<T> V = tile_view(F, cur, tile);
+        for (int tx = 0; tx < tl / VEC; ++tx) {
+            const LaneInfo<VEC> L = load_tile_lanes<T, VEC>(F, (tile * tl) / VEC + tx, tile_minfin[tile]);
+            if (!L.active) continue;
+            uint32_t bad = 0;
+            for (const CheckBin &bin : g.bins)
+                for (int32_t t = 0; t < 3; ++t)
+                    bad |= run_fused_bin_any<T, VEC>(V, F.nbr, L, tx * VEC, bin, t, 3, 0, 0);
+            for (int k = 0; k < VEC; ++k)
+                if (bad >> k & 1) P.unsat[0][L.l0 + k] = 1;
         }
     };
-    refill(0, 0);
-    int64_t step = 0;
-    for (; ctrl[CTRL_REMAINING] > 0; ++step) {
-        if (step > (frames + lanes) * (int64_t)(maxiter + 3)) return -1;
-        const int cur = step & 1;
-        const int32_t minfin = ctrl[CTRL_MINFIN];
-        for (int tile = 0; tile < F.tiles; ++tile) {
-            const TileView<T> V = tile_view(F, cur, tile);
-            for (int tx = 0; tx < tl / VEC; ++tx) {
-                LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, (tile * tl) / VEC + tx);
-                mark_post_lanes<T, VEC>(F, L, minfin);
-                if (!L.active) continue;
-                uint32_t bad = 0;
-                for (const CheckBin &bin : g.bins)
-                    for (int32_t t = 0; t < 3; ++t)
-                        bad |= run_fused_bin_any<T, VEC>(V, F.nbr, L, tx * VEC, bin, t, 3, 0, 0);
-                for (int k = 0; k < VEC; ++k)
-                    if (bad >> k & 1) P.unsat[cur][L.l0 + k] = 1;
+    auto bookkeep = [&](int tile) {          // tile_bookkeep of qr_decode_fused.cu, one lane after the other
+        const int32_t minfin_used = tile_minfin[tile];
+        int32_t listed = 0;
+        for (int l = 0; l < tl; ++l) {
+            const int lane = tile * tl + l;
+            LaneState s = st[lane];
+            const BkDecision d = bk_decide(s, unsat[lane], maxiter);
+            if (d.fin_ok || d.fin_fail) {
+                success[s.frame] = d.fin_ok ? 1 : 0;
+                iters[s.frame] = d.fin_ok ? s.iter : maxiter;
+                if (d.fin_ok && s.iter > 0 && s.iter < ctrl[CTRL_MINFIN]) ctrl[CTRL_MINFIN] = s.iter;
+                stats[0] += (unsigned long long)s.iter;
+                ctrl[CTRL_REMAINING] -= 1;
+                RefillEntry e;
+                e.lane = l; e.retire = s.frame;
+                const int32_t nf = ctrl[CTRL_NEXT_FRAME]++;
+                e.frame = (int64_t)nf < frames ? nf : -1;
+                e.post_valid = (F.post && stores_post(s.iter, maxiter, minfin_used)) ? 1 : 0;
+                rlist[(size_t)tile * tl + listed++] = e;
+                s.frame = e.frame; s.iter = 0; s.fresh = e.frame >= 0 ? 1 : 0;
+            } else if (s.frame >= 0) {
+                s.iter += 1; s.fresh = 0;
             }
+            s.retire = -1;
+            st[lane] = s;
+            unsat[lane] = 0;
         }
-        for (int jv = 0; jv < lanes / VEC; ++jv) {
-            LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
-            decide_lanes<T, VEC>(P, cur, L);
-            fused_note_finishers<T, VEC>(F, cur ^ 1, L, minfin);
-            bookkeep_lanes<T, VEC>(P, cur, (int32_t)step, L);
+        rcount[tile] = listed;
+        tile_minfin[tile] = ctrl[CTRL_MINFIN];
+    };
+    auto post_process = [&](int tile, int cur) {
+        for (int32_t ei = 0; ei < rcount[tile]; ++ei) {
+            const RefillEntry e = rlist[(size_t)tile * tl + ei];
+            if (e.post_valid && iters[e.retire] != 0) ++shipped_from_post;
+            for (int32_t n = 0; n < g.N; ++n) fused_pp_var_elem<T>(F, cur, e, tile, n);
+            for (int32_t ci = 0; ci < g.C; ++ci) fused_pp_chk_elem<T>(F, e, tile, ci);
+            ++completed;
         }
-        ctrl[CTRL_MINFIN] = ctrl[CTRL_MINFIN_NEXT];
-        if (ctrl[CTRL_FIN_STEP] == step) refill(cur ^ 1, cur);
+        rcount[tile] = 0;
+    };
+    const int lag = std::min(1, tiles - 1);    // (on the device PP follows BK through a ready queue: any order after BK is legal)
+    int64_t round = 0;
+    for (; completed < frames; ++round) {
+        if (round > (frames + lanes) * (int64_t)(maxiter + 3)) return -1;
+        const int cur = (int)(round & 1);
+        for (int t = 0; t < tiles; ++t) {
+            sweep(t, cur);
+            bookkeep(t);
+            const int pt = t >= lag ? t - lag : t - lag + tiles;
+            const int64_t pr = t >= lag ? round : round - 1;
+            if (pr >= 0) post_process(pt, (int)(pr & 1));
+        }
     }
     if (shipped_out) *shipped_out = shipped_from_post;
-    if (steps_out) *steps_out = step;
+    if (steps_out) *steps_out = round;
     return 0;
 }
 
@@ -305,6 +343,7 @@ void emu_demap_symbol(int bps, const double *a, const double *thr, const double 
     const int M = 1 << bps;
     const double sigma = sqrt(noise_var), s2 = sqrt(2.0) * sigma;
     std::vector<double> FYt(M + 1), delta(M), ghi(M), glo(M), pz(3 * M);
+    std::vector<float> g2hi(M), g2lo(M), pzf(3 * M);
     FYt[0] = 0; FYt[M] = 1;
     for (int i = 1; i < M; ++i) FYt[i] = mixture_cdf(a, p, M, s2, thr[i]);
     for (int i = 0; i < M; ++i) delta[i] = FYt[i + 1] - FYt[i];
@@ -313,10 +352,13 @@ void emu_demap_symbol(int bps, const double *a, const double *thr, const double 
         const double t2 = (i * step) * (i * step);
         ghi[i] = exp(-t2 / (2 * noise_var));
         glo[i] = exp(-t2);
+        g2hi[i] = (float)(t2 / (2 * noise_var) * 1.4426950408889634);
+        g2lo[i] = (float)(t2 * 1.4426950408889634);
     }
     for (int i = 0; i < 3 * M; ++i) {
         const int k = i - (M - 1);
         pz[i] = (k >= 0 && k < M) ? p[k] : 0.0;
+        pzf[i] = (float)pz[i];
     }
     const int32_t tn = 16385, jn = 8192;
     const double ty0 = a[0] - 9.0 * sigma, th = (a[M - 1] + 9.0 * sigma - ty0) / (tn - 1);
@@ -341,7 +383,7 @@ void emu_demap_symbol(int bps, const double *a, const double *thr, const double 
     m.FY_thr = FYt.data(); m.delta = delta.data(); m.bare = nullptr;
     m.inv_tab = tabF.data(); m.inv_pdf = tabf.data(); m.inv_n = tn; m.inv_y0 = ty0; m.inv_h = th;
     m.inv_jump = jump.data(); m.inv_jn = jn; m.uniform = 1; m.index_errors = nullptr;
-    TablesRef t{a, p, thr, FYt.data(), delta.data(), sign, ghi.data(), glo.data(), pz.data()};
+    TablesRef t{a, p, thr, FYt.data(), delta.data(), sign, ghi.data(), glo.data(), pz.data(), g2hi.data(), g2lo.data(), pzf.data()};
     for (int64_t s = 0; s < n; ++s) demap_symbol_any(m, t, n_hat[s], (int32_t)tx[s], mode, alpha, llr + s * bps);
 }
 

@@ -1,6 +1,8 @@
-"""Randomised differential test of the fused flooding-iteration schedule against the two-phase schedule:
-random (3, k)-regular and variable-regular-3 codes, frame counts, lane counts, iteration limits, noise levels,
-inconsistent syndromes.  fp64: success flags, iteration counts and posteriors must be BIT-identical (the two
+"""Randomised differential test of the fused flooding-iteration schedule (tile pipeline) against the two-phase
+schedule: random (3, k)-regular and variable-regular-3 codes, IRREGULAR variable degrees (1..10, extended neighbour
+records), frame counts, lane counts (several tiles, frames >> lanes so that lanes are refilled many times and the
+post-processing of one tile overlaps the sweep of the next), tile sizes, iteration limits, noise levels, inconsistent
+syndromes.  fp64: success flags, iteration counts and posteriors must be BIT-identical (the two
 schedules restate the same arithmetic); fp32: the same flags, iteration counts within 1, same hard decisions on
 converged frames.  Catches ordering bugs in the work claims, the bookkeeping and the two shipping paths."""
 import numpy as np
@@ -43,8 +45,18 @@ def mixed_check_degrees(codes, n, rng):
     return codes._finish(vsock, csock)
 
 
-@pytest.mark.parametrize("seed", range(12))
-def test_fused_equals_two_phase(seed):
+def irregular_variable_degrees(codes, n, rng):
+    """variable degrees drawn from {1, 2, 3, 4, 5, 10} (inline and extended neighbour records), check degrees <= 8"""
+    degs = [1, 2, 3, 4, 5, 10]
+    frac = rng.dirichlet(np.ones(len(degs)))
+    frac[2] += 1.0; frac /= frac.sum()
+    avg = float(np.dot(frac, degs))
+    c = int(np.ceil(n * avg / 6.0)) + 2                # average check degree ~6 (max <= 8 for these sizes)
+    return codes.irregular_ldpc(n, c, degs, list(frac), seed=int(rng.integers(1, 1 << 30)))
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_fused_equals_two_phase(seed, monkeypatch):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import qamreconciliation as qr
@@ -52,8 +64,12 @@ def test_fused_equals_two_phase(seed):
     from oracle import port as orc
     rng = np.random.default_rng(1000 + seed)
     n = int(rng.choice([96, 240, 648, 1296]))
-    kind = seed % 3
-    if kind == 0:
+    kind = seed % 5
+    if kind >= 3:
+        vid, cid = irregular_variable_degrees(codes, n, rng)               # any variable degree, mixed check degrees
+        if np.bincount(cid).max() > 8:
+            pytest.skip("drew a check of degree > 8")
+    elif kind == 0:
         vid, cid = codes.regular_ldpc(n, 3, 6, seed=seed)                 # check-regular: the specialised kernel
     elif kind == 1:
         vid, cid = codes.regular_ldpc(n, 3, 3, seed=seed)                 # (3,3): generic fused path, degree 3
@@ -63,7 +79,13 @@ def test_fused_equals_two_phase(seed):
     lanes = int(rng.choice([32, 64, 96, 128]))
     maxiter = int(rng.choice([0, 1, 3, 10, 25]))
     llr, synd = frames_for(orc, vid, cid, frames, rng)
+    if seed % 4 == 3:
+        monkeypatch.setenv("QAMRECON_FUSED_TILE", "64")                    # wider tiles
+    if seed % 2:
+        monkeypatch.setenv("QAMRECON_FUSED_PP_LAG", str(int(rng.integers(0, 4))))
+        monkeypatch.setenv("QAMRECON_FUSED_PP_ITEMS", str(int(rng.integers(1, 9))))
     dec = qr.Decoder(vid, cid)
+    assert dec.fused_eligible
     a = dec.decode_batch(llr, synd, maxiter, precision="fp64", lanes=lanes, schedule=0)
     b = dec.decode_batch(llr, synd, maxiter, precision="fp64", lanes=lanes, schedule=2)
     assert torch.equal(a[0], b[0]), (seed, "success")

@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--precisions", default="fp32")
     ap.add_argument("--maxiter", type=int, default=50)
     ap.add_argument("--stages", action="store_true")
-    ap.add_argument("--fused", default="32:1", help="tile:hints[:pipe[:prefetch[:rows_per_claim]]] combinations tried for schedule 2 (fused)")
+    ap.add_argument("--fused", default="32:1", help="tile:hints[:pp_lag[:pp_items[:rows_per_claim]]] combinations tried for schedule 2 (fused)")
     a = ap.parse_args()
     n, B = a.n, a.frames
     vid, cid = codes.regular_ldpc(n, 3, 6, seed=1)
@@ -52,7 +52,10 @@ def main():
     t_fe, (idx, nh, word) = timeit(lambda: nm.front_end_batch(y))
     t_sy, synd = timeit(lambda: mat.eval_syndrome_batch(word))
     t_df, llr = timeit(lambda: nm.demap_lappr_array_batch(nh, x, mode="fast", out_dtype=torch.float32))
+    t_d32, llr32 = timeit(lambda: nm.demap_lappr_array_batch(nh, x, mode="fast32", out_dtype=torch.float32))
     print(f"frames {B}  n {n}  snr {a.snr}")
+    print(f"demap(fast32,f32) {t_d32:8.2f} ms   max |fast32-fast| = {(llr32 - llr).abs().max().item():.3e}   "
+          f"max rel = {((llr32 - llr).abs() / llr.abs().clamp_min(1e-3)).max().item():.3e}")
     print(f"front_end {t_fe:8.2f} ms   syndrome {t_sy:8.2f} ms   demap(fast,f32) {t_df:8.2f} ms")
     if a.stages:
         t_de, llr_e = timeit(lambda: nm.demap_lappr_array_batch(nh, x, mode="exact", out_dtype=torch.float32), reps=1)
@@ -64,12 +67,10 @@ def main():
         for sched in [int(s) for s in a.schedules.split(",")]:
           for combo in (a.fused.split(",") if sched == 2 else [""]):
             if combo:
-                parts = (combo.split(":") + ["0", "0", "4"])[:5] if combo.count(":") < 4 else combo.split(":")
-                os.environ["QAMRECON_FUSED_RPC"] = parts[4]
-                os.environ["QAMRECON_FUSED_STATIC"] = parts[5] if len(parts) > 5 else "0"
-                os.environ["QAMRECON_FUSED_PREFETCH"] = parts[3]
+                parts = (combo.split(":") + ["1", "0", "4"])[:5] if combo.count(":") < 4 else combo.split(":")
                 os.environ["QAMRECON_FUSED_TILE"], os.environ["QAMRECON_FUSED_HINTS"] = parts[0], parts[1]
-                os.environ["QAMRECON_FUSED_PIPE"] = parts[2]
+                os.environ["QAMRECON_FUSED_PP_LAG"], os.environ["QAMRECON_FUSED_PP_ITEMS"] = parts[2], parts[3]
+                os.environ["QAMRECON_FUSED_RPC"] = parts[4]
             for lanes in [int(s) for s in a.lanes.split(",")]:
                 t, (ok, it, post) = timeit(lambda: dec.decode_batch(inp, synd, a.maxiter, precision=prec, lanes=lanes,
                                                                    schedule=sched))
