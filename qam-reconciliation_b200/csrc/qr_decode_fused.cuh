@@ -335,16 +335,17 @@ QR_HD uint32_t fused_item_lean(const char *llr_t, const char *cold_t, char *cnew
         for (int j = 0; j < HB; ++j) {
             const int i = i0 + j;
             if (i < D) {
+                NbrL q;
 #if defined(__CUDA_ARCH__)
-                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(rec + slot0 + i));
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(rec + slot0 + i));
+                q.llr_off = raw.x; q.o1_off = raw.y; q.o2_off = raw.z; q.first = raw.w;
 #else
-                const NbrL &r = rec[slot0 + i];
-                const uint4 q{r.llr_off, r.o1_off, r.o2_off, r.first};
+                q = rec[slot0 + i];
 #endif
-                first[j] = q.w;
-                ch[j] = ld_pol(reinterpret_cast<const VT *>(llr_t + q.x), pol_ld);
-                m1[j] = ld_pol(reinterpret_cast<const VT *>(cold_t + q.y), pol_ld);
-                m2[j] = ld_pol(reinterpret_cast<const VT *>(cold_t + q.z), pol_ld);
+                first[j] = q.first;
+                ch[j] = ld_pol(reinterpret_cast<const VT *>(llr_t + q.llr_off), pol_ld);
+                m1[j] = ld_pol(reinterpret_cast<const VT *>(cold_t + q.o1_off), pol_ld);
+                m2[j] = ld_pol(reinterpret_cast<const VT *>(cold_t + q.o2_off), pol_ld);
                 mo[j] = ld_pol(reinterpret_cast<const VT *>(own_t + (uint32_t)i * rowb), pol_ld);
             }
         }
