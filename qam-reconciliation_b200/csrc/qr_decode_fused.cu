@@ -141,7 +141,8 @@ __device__ __forceinline__ void tile_bookkeep(const FusedParams<T> &F, int32_t t
 // PP item `item` of (tile, round): rows [N item / R, N (item + 1) / R) of the variables and the same share of the
 // checks, for every lane of the tile's refill list.  One warp; lane i takes rows r0 + i, r0 + i + 32, ...; all loads
 // of a batch of kPPRows rows are issued before their stores.  `cur` = message buffer the sweep read.
-constexpr int kPPRows = 4;
+constexpr int kPPRows = 4;    // rows in flight per thread (measured on B200: 16 is SLOWER -- the column accesses of a refill
+                              // are 32-byte sectors at DRAM, and more of them in flight only crowd out the sweeps)
 
 template <typename T>
 __device__ __forceinline__ int32_t tile_pp_item(const FusedParams<T> &F, int32_t tile, int32_t item, int cur)
@@ -269,7 +270,7 @@ __device__ __forceinline__ void fused_initial_fill(const FusedParams<T> &F)
 template <typename T, int VEC, int DSEL, int VDEG>
 __device__ __forceinline__ uint32_t fused_claim(const FusedParams<T> &F, const TileView<T> &V, const LaneInfo<VEC> &L,
                                                 int32_t c0, int32_t c1, int32_t tx, int32_t tyw, int32_t wy,
-                                                uint64_t pol_ld, uint64_t pol_st)
+                                                uint64_t pol_ld, uint64_t pol_st, uint64_t pol_post = 0)
 {
     const DecodeParams<T> &P = F.P;
     uint32_t bad = 0;
@@ -285,8 +286,8 @@ __device__ __forceinline__ uint32_t fused_claim(const FusedParams<T> &F, const T
             char *post_t = reinterpret_cast<char *>(V.post) + lt4;
             const uint8_t *synd_t = V.synd + tx * VEC;
             for (int32_t ci = c0 + tyw; ci < c1; ci += wy) {
-                if (L.fresh) bad |= fused_item_lean<6, true>(llr_t, cold_t, cnew_t, post_t, synd_t, rec, ci, 6 * ci, V.tl, L.fresh, L.wpost, L.active, pol_ld, pol_st);
-                else bad |= fused_item_lean<6, false>(llr_t, cold_t, cnew_t, post_t, synd_t, rec, ci, 6 * ci, V.tl, 0u, L.wpost, L.active, pol_ld, pol_st);
+                if (L.fresh) bad |= fused_item_lean<6, true>(llr_t, cold_t, cnew_t, post_t, synd_t, rec, ci, 6 * ci, V.tl, L.fresh, L.wpost, L.active, pol_ld, pol_st, pol_post);
+                else bad |= fused_item_lean<6, false>(llr_t, cold_t, cnew_t, post_t, synd_t, rec, ci, 6 * ci, V.tl, 0u, L.wpost, L.active, pol_ld, pol_st, pol_post);
             }
             return bad;
         }
@@ -483,14 +484,15 @@ __global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __gri
                 L.wpost |= ((f >> 2) & 1u) << k;
             }
             const TileView<T> V = tile_view(F, round & 1, tile);
-            const uint64_t pol_ld = l2_policy(F.hints >= 2 ? 2 : 0), pol_st = l2_policy(F.hints >= 1 ? 1 : 0);
+            const uint64_t pol_ld = l2_policy(F.hints == 2 ? 2 : 0), pol_st = l2_policy(F.hints >= 1 ? 1 : 0);
+            const uint64_t pol_post = l2_policy(F.hints == 3 ? 2 : 0);   // (3: posterior columns kept for the refill)
             const int32_t claim_rows = wy * F.rows_per_claim, C = (int32_t)P.C;
             const int32_t c0 = w.chunk * claim_rows, c1 = min(c0 + claim_rows, C);
             const int32_t passes = F.rows_per_claim;
             for (int32_t r = 0; r < max(passes, 2); ++r) {
                 if (r < passes && L.active) {
                     const int32_t lo = c0 + r * wy, hi = min(lo + wy, c1);
-                    if (lo < hi) bad |= fused_claim<T, VEC, DSEL, VDEG>(F, V, L, lo, hi, tx, tyw, wy, pol_ld, pol_st);
+                    if (lo < hi) bad |= fused_claim<T, VEC, DSEL, VDEG>(F, V, L, lo, hi, tx, tyw, wy, pol_ld, pol_st, pol_post);
                 }
                 if (r == 0) {
                     issue_count();                                     // the claim before this one
@@ -580,7 +582,7 @@ static int run_batch_fused_v(qr_decoder *d, const DecodeParams<T> &P, cudaStream
     tl = std::min<int32_t>(tl, kFusedMaxTile);
     while (tl > 32 && (P.lanes % tl || (tl / VEC) > 32)) tl /= 2;   // a check row is shared by at most one warp
     const int32_t tiles = P.lanes / tl, tiles_max = d->lanes / 32;
-    constexpr int32_t kMaxPPItems = 64;
+    constexpr int32_t kMaxPPItems = 128;   // (7 bits in a ready-queue entry)
     if (!d->fused_ctl) {
         // per tile: f_done, pp_done, pp_expect, rcount, tile_minfin, bk_word (2 words); the per-lane flag bytes; the
         // refill lists; the PP ready queue
@@ -612,7 +614,7 @@ static int run_batch_fused_v(qr_decoder *d, const DecodeParams<T> &P, cudaStream
     F.rows_per_claim = d->fused_rpc > 0 ? d->fused_rpc : 4;
     F.dbg = getenv("QAMRECON_FUSED_DBG") ? atoi(getenv("QAMRECON_FUSED_DBG")) : 0;
     F.pp_items = d->fused_pp_items > 0 ? std::min(d->fused_pp_items, kMaxPPItems)
-                                       : (int32_t)std::min<int64_t>(kMaxPPItems, std::max<int64_t>(4, g->N / 1024));
+                                       : (int32_t)std::min<int64_t>(kMaxPPItems, std::max<int64_t>(4, g->N / 512));
     F.f_done = d->fused_ctl;
     F.pp_done = d->fused_ctl + tiles_max;
     F.pp_expect = d->fused_ctl + 2 * tiles_max;

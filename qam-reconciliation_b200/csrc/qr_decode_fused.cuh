@@ -316,7 +316,8 @@ struct alignas(16) NbrL {
 template <int D, bool ANYFRESH>
 QR_HD uint32_t fused_item_lean(const char *llr_t, const char *cold_t, char *cnew_t, char *post_t,
                                const uint8_t *synd_t, const NbrL *rec, int32_t ci, int32_t slot0, int32_t tl,
-                               uint32_t fresh, uint32_t wpost, uint32_t active, uint64_t pol_ld, uint64_t pol_st)
+                               uint32_t fresh, uint32_t wpost, uint32_t active, uint64_t pol_ld, uint64_t pol_st,
+                               uint64_t pol_post)
 {
     using VT = Vec<float, 4>;
     const uint32_t rowb = (uint32_t)tl * 4u;
@@ -370,7 +371,7 @@ QR_HD uint32_t fused_item_lean(const char *llr_t, const char *cold_t, char *cnew
 #else
                     const uint32_t off = rec[slot0 + i].llr_off;
 #endif
-                    *reinterpret_cast<VT *>(post_t + off) = pv;
+                    st_pol(reinterpret_cast<VT *>(post_t + off), pv, pol_post);
                 }
             }
         }
@@ -491,8 +492,17 @@ QR_HD void fused_pp_var_elem(const FusedParams<T> &F, int cur, const RefillEntry
         } else {
             const T *c = F.c2v[cur] + (int64_t)tile * P.E * F.tl + e.lane;
             T acc = ld_stream(&P.llr[at]);
-            for (int32_t q = P.var_ptr[n]; q < P.var_ptr[n + 1]; ++q)
-                acc = acc + ld_stream(&c[(int64_t)P.var_slot[q] * F.tl]);        // decoder.pyx:291-293, ascending edge id
+            const int32_t q0 = P.var_ptr[n], q1 = P.var_ptr[n + 1];
+            if (F.nbr_lean && q1 - q0 == 3) {
+                // float mode, lean item: the stored posterior is the first edge's ((llr + c[e1]) + c[e2]) + c[e0];
+                // the rebuilt one takes the same association, so both shipping paths give the same bits
+                acc = acc + ld_stream(&c[(int64_t)P.var_slot[q0 + 1] * F.tl]);
+                acc = acc + ld_stream(&c[(int64_t)P.var_slot[q0 + 2] * F.tl]);
+                acc = acc + ld_stream(&c[(int64_t)P.var_slot[q0] * F.tl]);
+            } else {
+                for (int32_t q = q0; q < q1; ++q)
+                    acc = acc + ld_stream(&c[(int64_t)P.var_slot[q] * F.tl]);    // decoder.pyx:291-293, ascending edge id
+            }
             store_output_llr(P.post_out, P.post_out_f64, idx, (double)acc);
         }
     }

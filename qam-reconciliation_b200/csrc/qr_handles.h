@@ -87,4 +87,8 @@ struct qr_mapper {
     int32_t *inv_jump = nullptr;   // InvTable::jump
     int32_t inv_jn = 0;
     double inv_y0 = 0, inv_h = 0;
+    double *inv32_F = nullptr;     // coarse copy for the fp32-grade demapper (InvTable32)
+    float *inv32_f = nullptr;
+    uint16_t *inv32_jump = nullptr;
+    double inv32_h = 0;
 };

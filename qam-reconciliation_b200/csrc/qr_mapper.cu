@@ -21,6 +21,7 @@ static MapperView view_of(const qr_mapper *m)
     v.inv_tab = m->inv_tab; v.inv_pdf = m->inv_pdf; v.inv_n = m->inv_n; v.inv_y0 = m->inv_y0; v.inv_h = m->inv_h;
     v.inv_jump = m->inv_jump; v.inv_jn = m->inv_jn;
     v.uniform = m->uniform;
+    v.inv32_F = m->inv32_F; v.inv32_f = m->inv32_f; v.inv32_jump = m->inv32_jump; v.inv32_h = m->inv32_h;
     v.index_errors = m->d_index_errors;
     return v;
 }
@@ -73,6 +74,28 @@ __global__ void k_fill_inv_table(MapperView m, double *tab, double *pdf, int32_t
         tab[j] = mixture_cdf(m.constellation, m.probabilities, m.order, m.s2, y0 + j * h);
         pdf[j] = mixture_pdf(m.constellation, m.probabilities, m.order, m.sigma, y0 + j * h);
     }
+}
+
+__global__ void k_fill_inv32(MapperView m, double *F, float *f, double y0, double h)
+{
+    const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < kInv32N) {
+        F[j] = mixture_cdf(m.constellation, m.probabilities, m.order, m.s2, y0 + j * h);
+        f[j] = (float)mixture_pdf(m.constellation, m.probabilities, m.order, m.sigma, y0 + j * h);
+    }
+}
+
+__global__ void k_fill_jump32(const double *__restrict__ F, uint16_t *__restrict__ jump)
+{
+    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > kInv32J + 1) return;
+    const double v = (double)t / (double)kInv32J;
+    int32_t lo = 0, hi = kInv32N;           // invariant: F[lo] <= v (or lo == 0), F[hi] > v (or hi == N)
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (F[mid] <= v) lo = mid; else hi = mid;
+    }
+    jump[t] = (uint16_t)lo;
 }
 
 // jump[t] = largest grid index g with tab[g] <= t / jn (0 if none): see InvTable::jump
@@ -142,8 +165,14 @@ __global__ void __launch_bounds__(256) k_demap32(MapperView m, const double *__r
                                                  double alpha, OUT *__restrict__ llr)
 {
     __shared__ SharedTables s;
+    __shared__ double s_F[kInv32N];
+    __shared__ float s_f[kInv32N];
+    __shared__ uint16_t s_jump[kInv32J + 2];
+    for (int i = threadIdx.x; i < kInv32N; i += blockDim.x) { s_F[i] = m.inv32_F[i]; s_f[i] = m.inv32_f[i]; }
+    for (int i = threadIdx.x; i < kInv32J + 2; i += blockDim.x) s_jump[i] = m.inv32_jump[i];
     stage_tables(m, s);
-    const TablesRef t = tables_ref(s);
+    TablesRef t = tables_ref(s);
+    t.t32 = InvTable32{s_F, s_f, s_jump, m.inv_y0, m.inv32_h};
     for (int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sidx < n;
          sidx += (int64_t)gridDim.x * blockDim.x) {
         double out[BPS];
@@ -292,6 +321,18 @@ int qr_mapper_create(int bits_per_symbol, const double *h_constellation, const d
         QR_CUDA_CHECK(cudaMalloc((void **)&m->inv_jump, (size_t)(m->inv_jn + 2) * sizeof(int32_t)));
         qr::k_fill_jump_table<<<(m->inv_jn + 1 + 255) / 256, 256>>>(m->inv_tab, m->inv_n, m->inv_jump, m->inv_jn);
         QR_CUDA_CHECK(cudaGetLastError());
+        // coarse copy for the fp32-grade demapper (same span, kInv32N points)
+        m->inv32_h = (h_constellation[M - 1] + 9.0 * m->sigma - m->inv_y0) / (qr::kInv32N - 1);
+        QR_CUDA_CHECK(cudaMalloc((void **)&m->inv32_F, qr::kInv32N * sizeof(double)));
+        QR_CUDA_CHECK(cudaMalloc((void **)&m->inv32_f, qr::kInv32N * sizeof(float)));
+        QR_CUDA_CHECK(cudaMalloc((void **)&m->inv32_jump, (qr::kInv32J + 2) * sizeof(uint16_t)));
+        {
+            qr::MapperView v = qr::view_of(m);
+            qr::k_fill_inv32<<<(qr::kInv32N + 255) / 256, 256>>>(v, m->inv32_F, m->inv32_f, m->inv_y0, m->inv32_h);
+            QR_CUDA_CHECK(cudaGetLastError());
+            qr::k_fill_jump32<<<(qr::kInv32J + 2 + 255) / 256, 256>>>(m->inv32_F, m->inv32_jump);
+            QR_CUDA_CHECK(cudaGetLastError());
+        }
         QR_CUDA_CHECK(cudaDeviceSynchronize());
         return QR_OK;
     };
@@ -313,6 +354,7 @@ void qr_mapper_destroy(qr_mapper *m)
         cudaFree(m->grid_y);
         cudaFree(m->inv_tab);
         cudaFree(m->inv_jump);
+        cudaFree(m->inv32_F); cudaFree(m->inv32_f); cudaFree(m->inv32_jump);
     }
     delete m;
 }

@@ -32,6 +32,10 @@ struct MapperView {
     double inv_y0, inv_h;
     const int32_t *inv_jump;      // see InvTable::jump
     int32_t inv_jn;
+    const double *inv32_F;        // InvTable32 (global copies, staged into shared memory by k_demap32)
+    const float *inv32_f;
+    const uint16_t *inv32_jump;
+    double inv32_h;
     int32_t uniform;              // constellation points equally spaced (always true for PAMAlphabet): enables E^m G[m]
     int32_t *index_errors;        // device counter of caller-supplied symbol / region indices found out of range
 };
@@ -59,6 +63,17 @@ struct InvTable {
     // search for a target to the few grid cells of its bin instead of a binary search over the whole region
     const int32_t *jump = nullptr;
     int32_t jn = 0;
+};
+
+// the fp32-grade demapper's own, COARSE copy of that grid (1025 points: 14 KB, staged in shared memory by k_demap32,
+// where a lookup costs ~30 cycles instead of an L2 round trip): F as double (target - F is a cancellation), the
+// density as float, the jump table as 16-bit indices
+constexpr int kInv32N = 1025, kInv32J = 1024;
+struct InvTable32 {
+    const double *F;
+    const float *f;
+    const uint16_t *jump;     // [kInv32J + 2]
+    double y0, h;
 };
 
 // rounding-exact multiply/add: the reference is compiled without FMA contraction
@@ -536,32 +551,36 @@ static QR_HD_NOINLINE double g_inv_slow_path(const double *a, const double *p, c
 // root of F_Y(y) = target to ~1e-10 where the density is not vanishing; everything else (saturated targets, deep
 // tails, targets outside the table) goes through g_inv_fast, which ends on the reference's cell
 QR_HD double g_inv_f32grade(const double *a, const double *p, const double *thr, const double *FYt, int order,
-                            double sigma, double s2, double target, int32_t region, const InvTable tab)
+                            double sigma, double s2, double target, int32_t region, const InvTable32 t32,
+                            const InvTable tab)
 {
     if (region > 0 && target == FYt[region]) return thr[region];
     if (region < order - 1 && target == FYt[region + 1]) return thr[region + 1];
-    if (target > 0.0 && target < 1.0 && tab.n > 1 && tab.f && tab.jump && target >= tab.F[0] &&
-        target < tab.F[tab.n - 1]) {
-        const int32_t t = (int32_t)(target * tab.jn);       // exact: jn is a power of two
-        int32_t lo = tab.jump[t], hi = tab.jump[t + 1] + 1; // F[lo] <= t / jn <= target < (t + 1) / jn < F[hi]
-        if (hi > tab.n - 1) hi = tab.n - 1;
+    if (target > 0.0 && target < 1.0 && t32.F && target >= t32.F[0] && target < t32.F[kInv32N - 1]) {
+        const int32_t t = (int32_t)(target * kInv32J);     // exact: a power of two
+        int32_t lo = t32.jump[t], hi = (int32_t)t32.jump[t + 1] + 1;   // F[lo] <= t / J <= target < (t + 1) / J < F[hi]
+        if (hi > kInv32N - 1) hi = kInv32N - 1;
         while (hi - lo > 1) {
             const int32_t mid = (lo + hi) >> 1;
-            if (tab.F[mid] <= target) lo = mid; else hi = mid;
+            if (t32.F[mid] <= target) lo = mid; else hi = mid;
         }
-        const double F0 = tab.F[lo], F1 = tab.F[hi], d0 = tab.f[lo], d1 = tab.f[hi];
+        const double F0 = t32.F[lo], F1 = t32.F[hi];
+        const float d0 = t32.f[lo], d1 = t32.f[hi];
         const double dF = F1 - F0, d = target - F0;
-        if (dF > 1e-30 && (d0 < d1 ? d0 : d1) > 1e-6) {
+        if (dF > 1e-30 && (d0 < d1 ? d0 : d1) > 1e-5f) {
             // the two differences above are the cancellations that need double; the cubic itself is solved in float
-            const float hf = (float)tab.h, dFf = (float)dF, df = (float)d;
-            const float A = hf * (float)d0, B = hf * (float)d1;
+            const float hf = (float)t32.h, dFf = (float)dF, df = (float)d;
+            const float A = hf * d0, B = hf * d1;
             const float c2 = 3.0f * dFf - 2.0f * A - B, c3 = A + B - 2.0f * dFf;     // cubic Hermite through (F, f) at both ends
             float sx = df * rcp_f32(dFf);
-            const float G = sx * fmaf(sx, fmaf(sx, c3, c2), A);
-            const float Gp = fmaf(sx, fmaf(3.0f * sx, c3, 2.0f * c2), A);
-            sx -= (G - df) * rcp_f32(Gp);
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const float G = sx * fmaf(sx, fmaf(sx, c3, c2), A);
+                const float Gp = fmaf(sx, fmaf(3.0f * sx, c3, 2.0f * c2), A);
+                sx -= (G - df) * rcp_f32(Gp);
+            }
             sx = fminf(fmaxf(sx, 0.0f), 1.0f);
-            return fma((double)sx, tab.h, fma((double)lo, tab.h, tab.y0));
+            return fma((double)sx, t32.h, fma((double)lo, t32.h, t32.y0));
         }
     }
     return g_inv_slow_path(a, p, thr, FYt, order, sigma, s2, target, region, tab);
@@ -608,6 +627,7 @@ struct TablesRef {
     // fp32-grade demapper: (m step)^2 c log2(e) for c = 1 / 2 sigma^2 (g2hi) and c = 1 (g2lo, the reference's
     // undivided k < j exponent), and the zero-padded probabilities, as floats
     const float *g2hi = nullptr, *g2lo = nullptr, *pzf = nullptr;
+    InvTable32 t32{nullptr, nullptr, nullptr, 0.0, 0.0};     // coarse inverse table (shared memory in k_demap32)
 };
 
 // demap_lappr (noisemapper.pyx:450-540) for ONE symbol: Bob's metric n_hat, Alice's symbol j -> bps
@@ -626,7 +646,7 @@ QR_HD void demap_symbol(const MapperView &m, const TablesRef &s, double nv, int3
     for (int i = 0; i < m.order; ++i) {
         const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
         const InvTable tab{m.inv_tab, m.inv_pdf, m.inv_n, m.inv_y0, m.inv_h, m.inv_jump, m.inv_jn};
-        const double yh = grade32 ? g_inv_f32grade(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, i, tab)
+        const double yh = grade32 ? g_inv_f32grade(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, i, s.t32, tab)
                           : fast  ? g_inv_fast(s.a, s.p, s.thr, s.FYt, m.order, m.sigma, m.s2, target, 1e-9, i, tab)
                                   : g_inv_exact(s.a, s.p, m.order, m.s2, target, 1e-9);
         double sum = 0;
@@ -736,7 +756,7 @@ QR_HD void demap_symbol_f32grade(const MapperView &m, const TablesRef &s, double
 #pragma unroll
     for (int i = 0; i < M; ++i) {
         const double target = inv_target(s.sign, s.FYt, s.delta, nv, i);
-        const double yh = g_inv_f32grade(s.a, s.p, s.thr, s.FYt, M, m.sigma, m.s2, target, i, tab);
+        const double yh = g_inv_f32grade(s.a, s.p, s.thr, s.FYt, M, m.sigma, m.s2, target, i, s.t32, tab);
         const double dd = yh - aj;
         const float uh = (float)(dd * k_hi), ul = (float)(dd * k_lo);
         double w;

@@ -144,6 +144,7 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     P.post_out = post; P.post_out_f64 = post_dtype == QR_F64;
     P.ctrl = ctrl.data(); P.stats = stats; P.work = nullptr; P.refill_list = nullptr;
     F.nbr = reinterpret_cast<const Nbr4 *>(g.slot_nbr.data());
+    F.nbr_lean = nullptr;
     F.c2v[0] = c2v0.data(); F.c2v[1] = c2v1.data();
     const int tiles = lanes / tl;
     F.tl = tl; F.tiles = tiles; F.hints = 0; F.rows_per_claim = 2; F.pp_items = 3; F.dbg = 0;
@@ -384,6 +385,25 @@ void emu_demap_symbol(int bps, const double *a, const double *thr, const double 
     m.inv_tab = tabF.data(); m.inv_pdf = tabf.data(); m.inv_n = tn; m.inv_y0 = ty0; m.inv_h = th;
     m.inv_jump = jump.data(); m.inv_jn = jn; m.uniform = 1; m.index_errors = nullptr;
     TablesRef t{a, p, thr, FYt.data(), delta.data(), sign, ghi.data(), glo.data(), pz.data(), g2hi.data(), g2lo.data(), pzf.data()};
+    // the coarse copy k_demap32 stages in shared memory
+    const double h32 = (a[M - 1] + 9.0 * sigma - ty0) / (kInv32N - 1);
+    std::vector<double> F32(kInv32N);
+    std::vector<float> f32(kInv32N);
+    std::vector<uint16_t> j32(kInv32J + 2);
+    for (int32_t j = 0; j < kInv32N; ++j) {
+        F32[j] = mixture_cdf(a, p, M, s2, ty0 + j * h32);
+        f32[j] = (float)mixture_pdf(a, p, M, sigma, ty0 + j * h32);
+    }
+    for (int32_t tt = 0; tt <= kInv32J + 1; ++tt) {
+        const double v = (double)tt / (double)kInv32J;
+        int32_t lo = 0, hi = kInv32N;
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (F32[mid] <= v) lo = mid; else hi = mid;
+        }
+        j32[tt] = (uint16_t)lo;
+    }
+    t.t32 = InvTable32{F32.data(), f32.data(), j32.data(), ty0, h32};
     for (int64_t s = 0; s < n; ++s) demap_symbol_any(m, t, n_hat[s], (int32_t)tx[s], mode, alpha, llr + s * bps);
 }
 
