@@ -10,8 +10,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
+#include <thread>
 #include <type_traits>
+#include <vector>
 
 // Row loads of a fused item are issued in batches of FUSED_BATCH_EDGES edges (4 loads each).  Measured on B200
 // (2048 frames x 50 iterations, 1024 lanes, 128 registers, 2 CTAs/SM): batches of 3 edges 63.7 ms, 4 edges 59.8 ms,
@@ -362,44 +365,66 @@ __global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __gri
     grid.sync();
 
     __shared__ WarpCtl s_ctl[kFBlock / 32];
+    // DISCIPLINE for the control block: lane 0 writes, __syncwarp(), every lane reads.  (Lanes of a warp are not in
+    // lock step: "all lanes write the same value" races with the next update of the same field.)
     volatile WarpCtl &w = s_ctl[threadIdx.x >> 5];
     const int32_t lid = threadIdx.x & 31;
     const uint32_t cpt = (uint32_t)(((int32_t)P.C + (32 / (F.tl / VEC)) * F.rows_per_claim - 1) / ((32 / (F.tl / VEC)) * F.rows_per_claim));
-    using Flags = Vec<uint8_t, VEC>;
+    const int32_t frames = (int32_t)P.frames;
 
-    auto set_coord = [&](unsigned long long q, bool next) {
+    // claim id -> coordinates (lane 0)
+    auto set_coord0 = [&](unsigned long long q, bool next) {
         const uint32_t q32 = (uint32_t)q, per_round = cpt * (uint32_t)F.tiles;
         const uint32_t round = q32 / per_round, rem = q32 - round * per_round, tile = rem / cpt;
         if (next) { w.n_round = (int32_t)round; w.n_tile = (int32_t)tile; w.n_chunk = (int32_t)(rem - tile * cpt); }
         else { w.round = (int32_t)round; w.tile = (int32_t)tile; w.chunk = (int32_t)(rem - tile * cpt); }
     };
-    // ---- completion counts
-    auto settle_count = [&]() {          // the count issued a claim ago has arrived: the LAST finisher of a sweep runs BK
-        if (w.cnt_tile < 0) return;
-        if ((uint32_t)(w.cnt_val + 1) == cpt * (uint32_t)(w.cnt_round + 1)) {
-            __threadfence();                                       // acquire: every claim of the sweep is visible
-            tile_bookkeep_cold<T>(F, w.cnt_tile, w.cnt_round);
-        }
-        w.cnt_tile = -1;
+    // what a claim needs to know before it starts (lane 0): exit flag, ticket slot, the tile's words
+    auto load_pre0 = [&](int32_t tile) {
+        const int32_t done = ld_volatile(&P.ctrl[CTRL_COMPLETED]);
+        const unsigned long long slot = *reinterpret_cast<const volatile unsigned long long *>(&F.ppq[w.ticket % (uint32_t)F.ppq_size]);
+        const unsigned long long bk = ld_acquire_u64(&F.bk_word[tile]);
+        const int32_t ppd = ld_volatile(&F.pp_done[tile]);
+        w.done = done; w.slot = slot; w.bk = bk; w.ppd = ppd;
     };
-    auto issue_count = [&]() {
-        if (w.sig_tile < 0) return;
+    auto tile_ready = [&](int32_t round) {         // (uniform: reads only)
+        const unsigned long long bk = w.bk;
+        return round == 0 || ((int32_t)(uint32_t)bk >= round && w.ppd >= (int32_t)(bk >> 32));
+    };
+    // ---- completion counts: sig_* = finished claim not yet counted; cnt_* = count issued
+    auto settle_count = [&]() {          // whoever finished a sweep LAST runs its bookkeeping
+        __syncwarp();
+        const int32_t ct = w.cnt_tile, cr = w.cnt_round;
+        if (ct < 0) return;
+        const bool last = (uint32_t)(w.cnt_val + 1) == cpt * (uint32_t)(cr + 1);
+        __syncwarp();
+        if (lid == 0) w.cnt_tile = -1;
+        __syncwarp();
+        if (last) {
+            __threadfence();                                       // acquire: every claim of the sweep is visible
+            tile_bookkeep_cold<T>(F, ct, cr);
+        }
+    };
+    int32_t cnt_r = 0;                   // lane 0: result of the count just issued, not yet in the control block
+    auto issue_count = [&](bool commit) {
+        __syncwarp();
+        const int32_t st = w.sig_tile, sr = w.sig_round;
+        if (st < 0) return;
         settle_count();
         __threadfence();                                           // release: messages and flags before the count
         __syncwarp();
-        int32_t v = 0;
-        if (lid == 0) v = atomicAdd(&F.f_done[w.sig_tile], 1);
-        w.cnt_val = __shfl_sync(0xffffffffu, v, 0);
-        w.cnt_tile = w.sig_tile; w.cnt_round = w.sig_round;
-        w.sig_tile = -1;
+        if (lid == 0) {
+            cnt_r = atomicAdd(&F.f_done[st], 1);                   // (its round trip overlaps the next pass unless committed here)
+            if (commit) w.cnt_val = cnt_r;
+            w.cnt_tile = st; w.cnt_round = sr;
+            w.sig_tile = -1;
+        }
+        __syncwarp();
     };
-    // ---- PP service
-    auto take_ticket = [&]() {
-        uint32_t t = 0;
-        if (lid == 0) t = (uint32_t)atomicAdd(&P.ctrl[CTRL_PP_HEAD], 1);
-        w.ticket = __shfl_sync(0xffffffffu, t, 0);
-    };
-    auto serve_pp = [&](unsigned long long slot) -> bool {
+    // ---- PP service: the item behind this warp's ticket, if it has been published
+    auto serve_pp = [&]() -> bool {
+        __syncwarp();
+        const unsigned long long slot = w.slot;
         if ((uint32_t)(slot >> 32) != w.ticket + 1u) return false;
         __threadfence();                                           // acquire (the publisher released before writing the slot)
         const uint32_t e = (uint32_t)slot;                         // bits 8.. tile, bits 1..7 item, bit 0 parity of the sweep's round
@@ -411,21 +436,10 @@ __global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __gri
             const int32_t done = atomicAdd(&F.pp_done[tile], 1) + 1;
             // every item of this PP complete: its retired frames are fully written out
             if (done == ld_volatile(&F.pp_expect[tile]) && cnt) atomicAdd(&P.ctrl[CTRL_COMPLETED], cnt);
+            w.ticket = (uint32_t)atomicAdd(&P.ctrl[CTRL_PP_HEAD], 1);
         }
-        take_ticket();
+        __syncwarp();
         return true;
-    };
-    // ---- what a claim needs to know before it starts (prefetched during the previous claim, or loaded in place)
-    auto load_pre = [&](int32_t tile) {
-        const int32_t done = ld_volatile(&P.ctrl[CTRL_COMPLETED]);
-        const unsigned long long slot = *reinterpret_cast<const volatile unsigned long long *>(&F.ppq[w.ticket % (uint32_t)F.ppq_size]);
-        const unsigned long long bk = ld_acquire_u64(&F.bk_word[tile]);
-        const int32_t ppd = ld_volatile(&F.pp_done[tile]);
-        w.done = done; w.slot = slot; w.bk = bk; w.ppd = ppd;
-    };
-    auto tile_ready = [&](int32_t round) {
-        const unsigned long long bk = w.bk;
-        return round == 0 || ((int32_t)(uint32_t)bk >= round && w.ppd >= (int32_t)(bk >> 32));
     };
     auto load_flags = [&](int32_t tile) {
         const uint8_t *p = F.lane_flags + tile * F.tl + (lid % (F.tl / VEC)) * VEC;
@@ -433,46 +447,52 @@ __global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __gri
         else return (uint32_t)__ldcg(reinterpret_cast<const unsigned short *>(p));
     };
 
-    {
-        unsigned long long q = 0;
-        if (lid == 0) q = atomicAdd(reinterpret_cast<unsigned long long *>(P.work), 1ULL);
-        q = __shfl_sync(0xffffffffu, q, 0);
-        set_coord(q, false);
-        take_ticket();
+    if (lid == 0) {
+        const unsigned long long q = atomicAdd(reinterpret_cast<unsigned long long *>(P.work), 1ULL);
+        set_coord0(q, false);
+        w.ticket = (uint32_t)atomicAdd(&P.ctrl[CTRL_PP_HEAD], 1);
         w.sig_tile = -1; w.cnt_tile = -1;
-        load_pre(w.tile);
+        load_pre0(w.tile);
     }
-    const int32_t frames = (int32_t)P.frames;
+    __syncwarp();
     bool have_flags = false;
     uint32_t flags = 0, n_flags = 0;          // (per lane: the flag bytes of this thread's VEC lanes)
     for (;;) {
         // ---- A. exit, PP service, readiness of the claim's tile
+        __syncwarp();
         if (w.done >= frames) break;
-        if (serve_pp(w.slot)) { load_pre(w.tile); have_flags = false; continue; }
+        if (serve_pp()) {
+            if (lid == 0) load_pre0(w.tile);
+            have_flags = false;
+            continue;
+        }
         if (!tile_ready(w.round)) {
             // not ready: few tiles, or the tail of a batch.  Count what is pending (it may be what the tile waits
             // for), then poll, serving the PP queue meanwhile
-            issue_count();
+            issue_count(true);
             settle_count();
             bool gone = false;
             for (;;) {
-                load_pre(w.tile);
+                __syncwarp();
+                if (lid == 0) load_pre0(w.tile);
+                __syncwarp();
                 if (w.done >= frames) { gone = true; break; }
                 if (tile_ready(w.round)) break;
-                if (!serve_pp(w.slot)) __nanosleep(100);
+                if (!serve_pp()) __nanosleep(100);
             }
             if (gone) break;
             have_flags = false;
             continue;                                              // (re-check the slot with the fresh loads)
         }
         if (!have_flags) flags = load_flags(w.tile);
-        unsigned long long nq = 0;
+        unsigned long long nq = 0, p_slot = 0, p_bk = 0;
+        int32_t p_done = 0, p_ppd = 0;
         if (lid == 0) nq = atomicAdd(reinterpret_cast<unsigned long long *>(P.work), 1ULL);   // in flight during pass 0
         // ---- B. the claim
         uint32_t bad = 0;
+        const int32_t tile = w.tile, round = w.round;
         {
             const int32_t bx = F.tl / VEC, tx = lid % bx, tyw = lid / bx, wy = 32 / bx;
-            const int32_t tile = w.tile, round = w.round;
             LaneInfo<VEC> L;
             L.l0 = tile * F.tl + tx * VEC;
             L.active = L.fresh = L.wpost = L.fin_ok = L.fin_fail = L.upd = 0;
@@ -495,16 +515,26 @@ __global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __gri
                     if (lo < hi) bad |= fused_claim<T, VEC, DSEL, VDEG>(F, V, L, lo, hi, tx, tyw, wy, pol_ld, pol_st, pol_post);
                 }
                 if (r == 0) {
-                    issue_count();                                     // the claim before this one
-                    nq = __shfl_sync(0xffffffffu, nq, 0);
-                    set_coord(nq, true);
-                    load_pre(w.n_tile);                                // consumed after the next pass
-                    w.n_have_flags = 0;
-                } else if (r == 1) {
-                    if (w.done < frames && (uint32_t)(w.slot >> 32) != w.ticket + 1u && tile_ready(w.n_round)) {
-                        n_flags = load_flags(w.n_tile);
-                        w.n_have_flags = 1;
+                    issue_count(false);                                // the claim before this one
+                    if (lid == 0) {
+                        set_coord0(nq, true);
+                        // one batch of loads for the next claim, left in registers while pass 1 computes
+                        p_done = ld_volatile(&P.ctrl[CTRL_COMPLETED]);
+                        p_slot = *reinterpret_cast<const volatile unsigned long long *>(&F.ppq[w.ticket % (uint32_t)F.ppq_size]);
+                        p_bk = ld_acquire_u64(&F.bk_word[w.n_tile]);
+                        p_ppd = ld_volatile(&F.pp_done[w.n_tile]);
                     }
+                } else if (r == 1) {
+                    if (lid == 0) {
+                        w.cnt_val = cnt_r;
+                        w.done = p_done; w.slot = p_slot; w.bk = p_bk; w.ppd = p_ppd;
+                    }
+                    __syncwarp();
+                    const bool pf = w.done < frames && (uint32_t)(w.slot >> 32) != w.ticket + 1u && tile_ready(w.n_round);
+                    if (pf) n_flags = load_flags(w.n_tile);
+                    __syncwarp();
+                    if (lid == 0) w.n_have_flags = pf ? 1 : 0;
+                    __syncwarp();
                 }
             }
             // per-lane "some check unsatisfied" flags: OR over the warp's check rows, idempotent stores of 1
@@ -514,10 +544,14 @@ __global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __gri
                 for (int k = 0; k < VEC; ++k)
                     if (bad >> k & 1) P.unsat[0][tile * F.tl + tx * VEC + k] = 1;
             }
-            w.sig_tile = tile; w.sig_round = round;                    // counted after pass 0 of the next claim
         }
-        w.round = w.n_round; w.tile = w.n_tile; w.chunk = w.n_chunk;
+        __syncwarp();
         have_flags = w.n_have_flags != 0; flags = n_flags;
+        __syncwarp();
+        if (lid == 0) {
+            w.sig_tile = tile; w.sig_round = round;                    // counted after pass 0 of the next claim
+            w.round = w.n_round; w.tile = w.n_tile; w.chunk = w.n_chunk;
+        }
     }
 }
 
@@ -533,6 +567,41 @@ static int launch_fused(qr_decoder *d, const FusedParams<T> &F, cudaStream_t str
     FusedParams<T> Fc = F;
     void *args[] = {&Fc};
     QR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kFBlock), args, 0, stream));
+    if (const char *wd = getenv("QAMRECON_FUSED_WATCHDOG")) {
+        // debugging aid: if the kernel is still running after the given number of seconds, print the pipeline's
+        // control words (read on a second stream while the kernel runs)
+        const double limit = atof(wd);
+        cudaStream_t side;
+        cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+        const auto t0 = std::chrono::steady_clock::now();
+        while (cudaStreamQuery(stream) == cudaErrorNotReady) {
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (el > limit) {
+                std::vector<int32_t> ctrl(CTRL_WORDS), ctl(8 * (size_t)F.tiles);
+                unsigned long long q = 0;
+                cudaMemcpyAsync(ctrl.data(), F.P.ctrl, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, side);
+                cudaMemcpyAsync(&q, F.P.work, 8, cudaMemcpyDeviceToHost, side);
+                cudaStreamSynchronize(side);
+                fprintf(stderr, "[fused watchdog] %.1f s: frames %lld next_frame %d remaining %d minfin %d completed %d pp_head %d pp_reserve %d queue %llu cpt*tiles ? tiles %d R %d\n",
+                        el, (long long)F.P.frames, ctrl[CTRL_NEXT_FRAME], ctrl[CTRL_REMAINING], ctrl[CTRL_MINFIN], ctrl[CTRL_COMPLETED],
+                        ctrl[CTRL_PP_HEAD], ctrl[CTRL_PP_RESERVE], q, F.tiles, F.pp_items);
+                for (int t = 0; t < F.tiles && t < 8; ++t) {
+                    int32_t v[4]; unsigned long long bk = 0;
+                    cudaMemcpyAsync(&v[0], F.f_done + t, 4, cudaMemcpyDeviceToHost, side);
+                    cudaMemcpyAsync(&v[1], F.pp_done + t, 4, cudaMemcpyDeviceToHost, side);
+                    cudaMemcpyAsync(&v[2], F.pp_expect + t, 4, cudaMemcpyDeviceToHost, side);
+                    cudaMemcpyAsync(&v[3], F.rcount + t, 4, cudaMemcpyDeviceToHost, side);
+                    cudaMemcpyAsync(&bk, F.bk_word + t, 8, cudaMemcpyDeviceToHost, side);
+                    cudaStreamSynchronize(side);
+                    fprintf(stderr, "[fused watchdog] tile %d: f_done %d pp_done %d pp_expect %d rcount %d bk_rounds %u bk_expect %u\n", t, v[0], v[1],
+                            v[2], v[3], (unsigned)bk, (unsigned)(bk >> 32));
+                }
+                break;
+            }
+            std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        }
+        cudaStreamDestroy(side);
+    }
     return QR_OK;
 }
 
