@@ -529,6 +529,7 @@ int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decode
         if (const char *v = getenv("QAMRECON_FUSED_RPC")) d->fused_rpc = atoi(v);
         if (const char *v = getenv("QAMRECON_FUSED_PP_ITEMS")) d->fused_pp_items = atoi(v);
         if (const char *v = getenv("QAMRECON_FUSED_LEAN")) d->fused_lean = atoi(v);
+        if (const char *v = getenv("QAMRECON_FUSED_PARK")) d->fused_park = std::max(0, atoi(v));
         if (const char *v = getenv("QAMRECON_FUSED_STORE_POST")) d->fused_store_post = atoi(v);
         const size_t L = (size_t)lanes;
         QR_CUDA_CHECK(cudaMalloc(&d->c2v, (size_t)g->E * L * w));

@@ -61,40 +61,55 @@ __device__ __forceinline__ void tile_bookkeep(const FusedParams<T> &F, int32_t t
         const BkDecision d = bk_decide(s, unsat, P.maxiter);
         const bool fin = d.fin_ok || d.fin_fail;
         const uint32_t m_fin = __ballot_sync(0xffffffffu, fin);
-        const int32_t n_fin = __popc(m_fin), rank = __popc(m_fin & ((1u << lid) - 1u));
-        int32_t first_frame = 0;
-        if (n_fin) {
-            if (lid == 0) first_frame = atomicAdd(&P.ctrl[CTRL_NEXT_FRAME], n_fin);
-            first_frame = __shfl_sync(0xffffffffu, first_frame, 0);
-        }
+        const int32_t n_fin = __popc(m_fin);
         unsigned long long it_sum = fin ? (unsigned long long)s.iter : 0ULL;
         for (int o = 16; o > 0; o >>= 1) it_sum += __shfl_xor_sync(0xffffffffu, it_sum, o);
         if (fin) {
+            // decoder.pyx:431-436: the frame is done; its lane is parked until the sector group is released
             P.success[s.frame] = d.fin_ok ? 1 : 0;
             P.iters[s.frame] = d.fin_ok ? s.iter : P.maxiter;
             if (d.fin_ok && s.iter > 0) atomicMin(&P.ctrl[CTRL_MINFIN], s.iter);   // (0 iterations = input already consistent: no signal)
-            RefillEntry e;
-            e.lane = base + lid;
-            e.retire = s.frame;
-            const int32_t nf = first_frame + rank;
-            e.frame = (int64_t)nf < P.frames ? nf : -1;
-            e.post_valid = (F.post && stores_post(s.iter, P.maxiter, minfin_used)) ? 1 : 0;
-            list[listed + rank] = e;
-            s.frame = e.frame; s.iter = 0; s.fresh = e.frame >= 0 ? 1 : 0;
+            const int32_t pv = (F.post && stores_post(s.iter, P.maxiter, minfin_used)) ? 1 : 0;
+            // (a frame whose posterior was NOT stored is rebuilt from this sweep's messages: it cannot wait)
+            s.retire = s.frame; s.frame = -1; s.iter = pv; s.fresh = pv ? 0 : F.park_rounds;
         } else if (s.frame >= 0) {
             s.iter += 1;
             s.fresh = 0;
+            s.retire = -1;
+        } else if (s.retire >= 0) {
+            s.fresh += 1;                                           // parked: one more round waited
         }
-        s.retire = -1;
-        P.st[0][lane] = s;
-        P.unsat[0][lane] = 0;
-        next_iter[base / 32] = s.frame >= 0 ? s.iter : -1;
-        next_fresh[base / 32] = s.fresh;
         if (lid == 0 && n_fin) {
             atomicAdd(&P.stats[0], it_sum);
             atomicAdd(&P.ctrl[CTRL_REMAINING], -n_fin);
         }
-        listed += n_fin;
+        // which parked lanes are released now
+        const bool parked = s.frame < 0 && s.retire >= 0;
+        const uint32_t m_run = __ballot_sync(0xffffffffu, s.frame >= 0), m_park = __ballot_sync(0xffffffffu, parked);
+        const uint32_t m_aged = __ballot_sync(0xffffffffu, parked && s.fresh >= F.park_rounds);
+        const bool no_more = ld_volatile(&P.ctrl[CTRL_NEXT_FRAME]) >= (int32_t)min(P.frames, (int64_t)0x7fffffff);
+        const uint32_t m_rel = octets_to_release(m_run, m_park, m_aged, no_more);
+        const int32_t n_rel = __popc(m_rel), rank = __popc(m_rel & ((1u << lid) - 1u));
+        int32_t first_frame = 0;
+        if (n_rel) {
+            if (lid == 0) first_frame = atomicAdd(&P.ctrl[CTRL_NEXT_FRAME], n_rel);
+            first_frame = __shfl_sync(0xffffffffu, first_frame, 0);
+        }
+        if (m_rel >> lid & 1) {
+            RefillEntry e;
+            e.lane = base + lid;
+            e.retire = s.retire;
+            const int32_t nf = first_frame + rank;
+            e.frame = (int64_t)nf < P.frames ? nf : -1;
+            e.post_valid = s.iter;
+            list[listed + rank] = e;
+            s.frame = e.frame; s.iter = 0; s.fresh = e.frame >= 0 ? 1 : 0; s.retire = -1;
+        }
+        P.st[0][lane] = s;
+        P.unsat[0][lane] = 0;
+        next_iter[base / 32] = s.frame >= 0 ? s.iter : -1;
+        next_fresh[base / 32] = s.fresh;
+        listed += n_rel;
     }
     __syncwarp();
     // PP of this tile: R items into the ready queue (nothing when no frame finished: the common case below the
@@ -610,11 +625,13 @@ bool fused_eligible(const qr_graph *g)
     return !g->slot_nbr.empty() && g->max_cdeg <= kFusedMaxCheckDegree;
 }
 
-// QR_SCHED_AUTO: the fused schedule pays off when a lane tile's live set (messages read + LLRs) stays in L2 between
-// its d_v re-reads; beyond that it moves MORE bytes than the two-phase schedule (measured)
+// QR_SCHED_AUTO.  The fused schedule pays off when a lane tile's live set (messages read + LLRs) stays in L2 between
+// its d_v re-reads; beyond that it moves MORE bytes than the two-phase schedule (config 3: 75 MB per 32-lane tile,
+// config 4: 604 MB -- both run the two-phase kernel).  It is also only tuned for graphs whose variables all have
+// degree 3 (lean item, register-resident records); other graphs are eligible (QR_SCHED_FUSED) but not preferred.
 bool fused_preferred(const qr_graph *g, size_t w)
 {
-    if (!fused_eligible(g)) return false;
+    if (!fused_eligible(g) || g->var_deg != 3) return false;
     const size_t tile_bytes = (size_t)(g->E + g->N) * 32 * w;
     return tile_bytes <= ((size_t)72 << 20);
 }
@@ -682,6 +699,7 @@ static int run_batch_fused_v(qr_decoder *d, const DecodeParams<T> &P, cudaStream
     F.hints = d->fused_hints;
     F.rows_per_claim = d->fused_rpc > 0 ? d->fused_rpc : 4;
     F.dbg = getenv("QAMRECON_FUSED_DBG") ? atoi(getenv("QAMRECON_FUSED_DBG")) : 0;
+    F.park_rounds = d->fused_park;
     F.pp_items = d->fused_pp_items > 0 ? std::min(d->fused_pp_items, kMaxPPItems)
                                        : (int32_t)std::min<int64_t>(kMaxPPItems, std::max<int64_t>(4, g->N / 512));
     F.f_done = d->fused_ctl;

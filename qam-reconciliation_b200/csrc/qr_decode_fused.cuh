@@ -93,6 +93,8 @@ struct FusedParams {
     int32_t tiles;
     int32_t hints;       // L2 policy: 0 none, 1 stores evict-first, 2 + loads evict-last
     int32_t rows_per_claim;   // checks per thread and claim
+    int32_t park_rounds; // a finished lane waits up to this many rounds for the other lanes of its 8-lane sector group, so
+                         // that the group is shipped and refilled together (one sector per row for 8 frames); 0: never
     int32_t dbg;         // timing experiments (QAMRECON_FUSED_DBG): 1 no release fence (INCORRECT), 2 plain load of the tile word
     // tile pipeline (device arrays, [tiles] each; monotonic counters)
     int32_t pp_items;    // R: items per PP
@@ -153,6 +155,20 @@ QR_HD void st_pol(V *p, const V &val, uint64_t pol)
     (void)pol;
     *p = val;
 #endif
+}
+
+// Posterior of the lanes in `mask` only.  A PARKED lane (finished, waiting for its sector group to be refilled) keeps
+// its posterior column until it is shipped: neighbours in the same thread's lane vector must not overwrite it.
+template <typename T, int VEC>
+QR_HD void store_post_lanes(T *p, const Vec<T, VEC> &v, uint32_t mask, uint64_t pol)
+{
+    if (mask == (1u << VEC) - 1u) {
+        st_pol(reinterpret_cast<Vec<T, VEC> *>(p), v, pol);
+    } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+            if (mask >> k & 1) p[k] = v.v[k];
+    }
 }
 
 // pointers of one tile
@@ -281,7 +297,7 @@ QR_HD uint32_t fused_item(const TileView<T> &V, const LaneInfo<VEC> &L, int32_t 
                 }
                 // the check holding the variable's FIRST edge keeps the posterior of lanes that may finish now
                 if (L.wpost && (VDEG == 3 ? (((uint32_t)q[i].vp >> 28) & 3u) == 0 : nbr_own(q[i]) == 0))
-                    *reinterpret_cast<VT *>(V.post + (int64_t)nbr_var(q[i]) * tl + lt) = pv;
+                    store_post_lanes<T, VEC>(V.post + (int64_t)nbr_var(q[i]) * tl + lt, pv, L.wpost, 0);
             }
         }
     }
@@ -371,7 +387,7 @@ QR_HD uint32_t fused_item_lean(const char *llr_t, const char *cold_t, char *cnew
 #else
                     const uint32_t off = rec[slot0 + i].llr_off;
 #endif
-                    st_pol(reinterpret_cast<VT *>(post_t + off), pv, pol_post);
+                    store_post_lanes<float, 4>(reinterpret_cast<float *>(post_t + off), pv, wpost, pol_post);
                 }
             }
         }
@@ -463,6 +479,23 @@ QR_HD BkDecision bk_decide(const LaneState &s, int32_t unsat, int32_t maxiter)
     if (unsat == 0) d.fin_ok = true;                  // syndrome test passed on post_t (decoder.pyx:402-405, :431-433)
     else if (s.iter >= maxiter) d.fin_fail = true;    // decoder.pyx:435-436
     return d;
+}
+
+// ---- BATCHED REFILLS.  A refill moves COLUMNS of the lane-interleaved arrays: one 32-byte sector per element, i.e.
+// 8 lanes' worth of traffic for one lane.  So a finished lane is PARKED (LaneState: frame = -1, retire = the finished
+// frame, iter = its post_valid flag, fresh = rounds waited) and its group of 8 lanes -- the lanes that share sectors
+// -- is released together: when none of the 8 is running any more, when a parked lane has waited park_rounds, or
+// when the batch has no frame left to admit (then nothing is gained by waiting).  `running` / `parked` / `aged`: bit
+// per lane of the tile's 32-lane block, after this round's update.  Returns the lanes to release.
+QR_HD uint32_t octets_to_release(uint32_t running, uint32_t parked, uint32_t aged, bool no_more_frames)
+{
+    uint32_t rel = 0;
+    for (int o = 0; o < 4; ++o) {
+        const uint32_t m = 0xffu << (8 * o);
+        if (!(parked & m)) continue;
+        if (no_more_frames || !(running & m) || (aged & m)) rel |= parked & m;
+    }
+    return rel;
 }
 
 // ---- PP, one (listed lane, variable) element: ship post = llr + sum c2v[cur] of a retired frame (what the

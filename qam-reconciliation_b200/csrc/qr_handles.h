@@ -42,6 +42,7 @@ struct qr_decoder {
     void *fused_ppq = nullptr;       // ready queue of post-processing items
     void *fused_nbrl = nullptr;      // lean neighbour records of the float mode (built for fused_nbrl_tl lanes per tile)
     int fused_nbrl_tl = 0;
+    int fused_park = 1;              // rounds a finished lane waits for its sector group before it is refilled alone (QAMRECON_FUSED_PARK)
     int fused_lean = 1;              // 0: the generic item in float mode too (QAMRECON_FUSED_LEAN)
     int fused_hints = 1;     // L2 policy of the fused schedule: 0 none, 1 stores evict-first, 2 + loads evict-last
     uint8_t *synd = nullptr;

@@ -121,7 +121,8 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
 template <typename T, int VEC>
 static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *llr, int llr_dtype,
                               const uint8_t *synd, int64_t frames, int maxiter, uint8_t *success, int32_t *iters,
-                              void *post, int post_dtype, int64_t *steps_out, int store_post, int64_t *shipped_out)
+                              void *post, int post_dtype, int64_t *steps_out, int store_post, int64_t *shipped_out,
+                              int park_rounds = 2)
 {
     if (g.slot_nbr.empty() || g.max_cdeg > kFusedMaxCheckDegree || lanes % tl) return -2;
     std::vector<T> c2v0((size_t)g.E * lanes, (T)1e30), c2v1((size_t)g.E * lanes, (T)-3e30), llrw((size_t)g.N * lanes, (T)3e29);
@@ -147,7 +148,7 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     F.nbr_lean = nullptr;
     F.c2v[0] = c2v0.data(); F.c2v[1] = c2v1.data();
     const int tiles = lanes / tl;
-    F.tl = tl; F.tiles = tiles; F.hints = 0; F.rows_per_claim = 2; F.pp_items = 3; F.dbg = 0;
+    F.tl = tl; F.tiles = tiles; F.hints = 0; F.rows_per_claim = 2; F.pp_items = 3; F.dbg = 0; F.park_rounds = park_rounds;
     std::vector<T> postw((size_t)g.N * lanes, (T)-7e29);
     F.post = store_post ? postw.data() : nullptr;
     std::vector<int32_t> tile_minfin(tiles, 0x7fffffff), rcount(tiles, 0);
@@ -184,29 +185,47 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     auto bookkeep = [&](int tile) {          // tile_bookkeep of qr_decode_fused.cu, one lane after the other
         const int32_t minfin_used = tile_minfin[tile];
         int32_t listed = 0;
-        for (int l = 0; l < tl; ++l) {
-            const int lane = tile * tl + l;
-            LaneState s = st[lane];
-            const BkDecision d = bk_decide(s, unsat[lane], maxiter);
-            if (d.fin_ok || d.fin_fail) {
-                success[s.frame] = d.fin_ok ? 1 : 0;
-                iters[s.frame] = d.fin_ok ? s.iter : maxiter;
-                if (d.fin_ok && s.iter > 0 && s.iter < ctrl[CTRL_MINFIN]) ctrl[CTRL_MINFIN] = s.iter;
-                stats[0] += (unsigned long long)s.iter;
-                ctrl[CTRL_REMAINING] -= 1;
+        for (int base = 0; base < tl; base += 32) {
+            uint32_t m_run = 0, m_park = 0, m_aged = 0;
+            for (int l = 0; l < 32; ++l) {
+                const int lane = tile * tl + base + l;
+                LaneState s = st[lane];
+                const BkDecision d = bk_decide(s, unsat[lane], maxiter);
+                if (d.fin_ok || d.fin_fail) {
+                    success[s.frame] = d.fin_ok ? 1 : 0;
+                    iters[s.frame] = d.fin_ok ? s.iter : maxiter;
+                    if (d.fin_ok && s.iter > 0 && s.iter < ctrl[CTRL_MINFIN]) ctrl[CTRL_MINFIN] = s.iter;
+                    stats[0] += (unsigned long long)s.iter;
+                    ctrl[CTRL_REMAINING] -= 1;
+                    const int32_t pv = (F.post && stores_post(s.iter, maxiter, minfin_used)) ? 1 : 0;
+                    s.retire = s.frame; s.frame = -1; s.iter = pv; s.fresh = pv ? 0 : F.park_rounds;
+                } else if (s.frame >= 0) {
+                    s.iter += 1; s.fresh = 0; s.retire = -1;
+                } else if (s.retire >= 0) {
+                    s.fresh += 1;
+                }
+                const bool parked = s.frame < 0 && s.retire >= 0;
+                if (s.frame >= 0) m_run |= 1u << l;
+                if (parked) m_park |= 1u << l;
+                if (parked && s.fresh >= F.park_rounds) m_aged |= 1u << l;
+                st[lane] = s;
+                unsat[lane] = 0;
+            }
+            const bool no_more = ctrl[CTRL_NEXT_FRAME] >= frames;
+            const uint32_t m_rel = octets_to_release(m_run, m_park, m_aged, no_more);
+            for (int l = 0; l < 32; ++l) {
+                if (!(m_rel >> l & 1)) continue;
+                const int lane = tile * tl + base + l;
+                LaneState s = st[lane];
                 RefillEntry e;
-                e.lane = l; e.retire = s.frame;
+                e.lane = base + l; e.retire = s.retire;
                 const int32_t nf = ctrl[CTRL_NEXT_FRAME]++;
                 e.frame = (int64_t)nf < frames ? nf : -1;
-                e.post_valid = (F.post && stores_post(s.iter, maxiter, minfin_used)) ? 1 : 0;
+                e.post_valid = s.iter;
                 rlist[(size_t)tile * tl + listed++] = e;
-                s.frame = e.frame; s.iter = 0; s.fresh = e.frame >= 0 ? 1 : 0;
-            } else if (s.frame >= 0) {
-                s.iter += 1; s.fresh = 0;
+                s.frame = e.frame; s.iter = 0; s.fresh = e.frame >= 0 ? 1 : 0; s.retire = -1;
+                st[lane] = s;
             }
-            s.retire = -1;
-            st[lane] = s;
-            unsat[lane] = 0;
         }
         rcount[tile] = listed;
         tile_minfin[tile] = ctrl[CTRL_MINFIN];
