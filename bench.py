@@ -605,14 +605,14 @@ def extras(a, torch, qr, codes, dev, wl, barrier):
     # BASELINE config 3: irregular R = 0.2, n = 131070 (3 * 43690), 8-PAM, 100 iterations max, below its waterfall
     v3, c3 = codes.irregular_ldpc(131070, 104856, [3, 8], [0.9, 0.1], seed=3)
     cfg3 = np.zeros(8, dtype=np.uint8); cfg3[1::2] = 1
-    w = Workload(torch, qr, codes, dev, 0, v3, c3, 3, 3.0, cfg3, 1024, 100, "fp32", "fast", 512, 3, n_sets=1)
+    w = Workload(torch, qr, codes, dev, 0, v3, c3, 3, 3.0, cfg3, 1024, 100, "fp32", "fast", 1024, 3, n_sets=1)
     measure(w, "config3_irregular_n131070_8pam", e2e=False)
     del w
     torch.cuda.empty_cache()
     # BASELINE config 4: QKD scale, irregular R = 0.1, n = 2^20, 2-PAM, 60 iterations max
     v4, c4 = codes.irregular_ldpc(1 << 20, 943718, [3, 4, 10], [0.8, 0.15, 0.05], seed=4)
-    w = Workload(torch, qr, codes, dev, 0, v4, c4, 1, -12.0, np.array([0, 1], dtype=np.uint8), 256, 60, "fp32", "fast",
-                 256, 3, n_sets=1)
+    w = Workload(torch, qr, codes, dev, 0, v4, c4, 1, -12.0, np.array([0, 1], dtype=np.uint8), 512, 60, "fp32", "fast",
+                 512, 3, n_sets=1)
     measure(w, "config4_irregular_n1048576_2pam", e2e=False)
     del w
     torch.cuda.empty_cache()

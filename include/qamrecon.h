@@ -48,9 +48,12 @@ extern "C" {
 #define QR_SCHED_PERSISTENT 0 /* one cooperative kernel per batch, grid barriers between phases */
 #define QR_SCHED_LAUNCH 1     /* one check + one variable kernel launch per iteration */
 #define QR_SCHED_FUSED 2      /* check update + variable sums + syndrome test in ONE pass per iteration, two
-                                 message buffers, L2-sized lane tiles; needs variable degree 3 everywhere and
-                                 check degrees <= 8 (QR_ERR_INVALID otherwise); same results */
-#define QR_SCHED_AUTO 3       /* QR_SCHED_FUSED where the graph allows it, else QR_SCHED_PERSISTENT (the default) */
+                                 message buffers, L2-sized lane tiles, tile-pipelined bookkeeping and refills;
+                                 needs check degrees <= 8, variable degrees 1..64 and fewer than 2^27 variables
+                                 (QR_ERR_INVALID otherwise); same results */
+#define QR_SCHED_AUTO 3       /* the default: QR_SCHED_FUSED when every variable has degree 3 and a 32-lane tile of
+                                 the code fits L2 (config 2), else QR_SCHED_PERSISTENT, or QR_SCHED_LAUNCH on graphs
+                                 of more than 2 M edges */
 
 typedef struct qr_graph qr_graph;
 typedef struct qr_decoder qr_decoder;

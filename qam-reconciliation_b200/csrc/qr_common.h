@@ -63,6 +63,13 @@ struct qr_graph {
     // so a warp runs one unrolled code path; empty when every variable has the same degree
     std::vector<int32_t> var_work;   // [N]
     int32_t *d_var_work = nullptr;
+    // ... and, in that order, one bin per variable degree (CheckBin reused: degree, first position in var_work,
+    // count, first entry of vslot_sorted) with the variables' slot lists stored contiguously per bin: the variable
+    // phase walks a bin with compile-time degree and prefetches the next item's indices (irregular graphs only)
+    std::vector<qr::CheckBin> var_bins;
+    std::vector<int32_t> vslot_sorted;   // [E]
+    qr::CheckBin *d_var_bins = nullptr;
+    int32_t *d_vslot_sorted = nullptr;
     // fused schedule: per CSR slot a 16-byte neighbour record (Nbr4, qr_decode_fused.cuh); empty when the graph is
     // outside its limits (2^27 variables, variable degree 64)
     std::vector<int32_t> slot_nbr;   // [4 * E]

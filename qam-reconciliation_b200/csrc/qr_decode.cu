@@ -110,6 +110,17 @@ __device__ __forceinline__ void var_phase(const DecodeParams<T> &P, int cur, int
 // ---- work-stealing variants for the persistent kernel: rows are claimed in chunks of by*kRowsPerClaim from
 // a per-lane-tile counter, so a slow SM (far L2 die, unlucky DRAM pages) does not hold the grid barrier.
 constexpr int kRowsPerClaim = 8;
+// (irregular graphs, binned variable phase: a claim also pays the pipeline prologue of every degree bin it touches)
+constexpr int kVarRowsPerClaimBinned = 32;
+
+// Rows per claim: at least by * rows_min, and large enough that a CTA makes about 16 claims per phase -- every claim
+// costs two CTA barriers and an atomic round trip (config 4, 944k checks: 100 claims per CTA and phase at the
+// minimum size, 11 % of the phase).
+__device__ __forceinline__ int32_t claim_rows(int32_t rows, int32_t ctas_per_lane_tile, int32_t by, int32_t rows_min)
+{
+    const int32_t want = rows / max(1, ctas_per_lane_tile * 16);
+    return max(by * rows_min, (want + by - 1) / by * by);
+}
 
 template <typename T, int VEC, int DSEL>
 __device__ __forceinline__ void check_phase_dyn(const DecodeParams<T> &P, int cur, const Tiling tl,
@@ -119,7 +130,8 @@ __device__ __forceinline__ void check_phase_dyn(const DecodeParams<T> &P, int cu
     const int32_t G = gridDim.x;
     const int32_t gx = min(tl.nxt, G);
     const int32_t bxid = blockIdx.x % gx, byid = blockIdx.x / gx;
-    const int32_t claim = tl.by * kRowsPerClaim, C = (int32_t)P.C;
+    const int32_t C = (int32_t)P.C;
+    const int32_t claim = claim_rows(C, G / gx, tl.by, kRowsPerClaim);
     for (int32_t xt = bxid; xt < tl.nxt; xt += gx) {
         const int32_t jv = xt * tl.bx + tx;
         const LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
@@ -178,7 +190,8 @@ __device__ __forceinline__ void var_phase_dyn(const DecodeParams<T> &P, int cur,
     const int32_t G = gridDim.x;
     const int32_t gx = min(tl.nxt, G);
     const int32_t bxid = blockIdx.x % gx, byid = blockIdx.x / gx;
-    const int32_t claim = tl.by * kRowsPerClaim, N = (int32_t)P.N;
+    const int32_t N = (int32_t)P.N;
+    const int32_t claim = claim_rows(N, G / gx, tl.by, (UNROLLED && P.var_bins) ? kVarRowsPerClaimBinned : kRowsPerClaim);
     for (int32_t xt = bxid; xt < tl.nxt; xt += gx) {
         const int32_t jv = xt * tl.bx + tx;
         LaneInfo<VEC> L = load_lane_info<T, VEC>(P, cur, jv);
@@ -190,7 +203,8 @@ __device__ __forceinline__ void var_phase_dyn(const DecodeParams<T> &P, int cur,
             __syncthreads();
             const int32_t n0 = *s_base;
             if (n0 >= N) break;
-            run_var_range<T, VEC, UNROLLED>(P, L, n0 + ty, tl.by, min(n0 + claim, N));
+            if (UNROLLED && P.var_bins) run_var_binned<T, VEC>(P, L, n0, min(n0 + claim, N), ty, tl.by);
+            else run_var_range<T, VEC, UNROLLED>(P, L, n0 + ty, tl.by, min(n0 + claim, N));
         }
         if (byid == 0 && ty == 0) bookkeep_lanes<T, VEC>(P, cur, step, L);
     }
@@ -385,6 +399,7 @@ static DecodeParams<T> make_params(const qr_decoder *d, const void *llr, int llr
     P.var_ptr = g->d_var_ptr;
     P.var_slot = g->d_var_slot;
     P.var_work = g->d_var_work;
+    P.var_bins = g->d_var_bins; P.n_var_bins = (int32_t)g->var_bins.size(); P.vslot_sorted = g->d_vslot_sorted;
     P.N = g->N; P.C = g->C; P.E = g->E;
     P.var_deg = g->var_deg;
     // a batch smaller than the workspace uses a narrower layout, so no CTA is left with idle lanes only
@@ -426,7 +441,11 @@ template <typename T, int DSEL, int VEC = Prec<T>::VEC>
 static int run_batch_t(qr_decoder *d, const DecodeParams<T> &P, cudaStream_t stream)
 {
     const Tiling tl = make_tiling<VEC>(P.lanes);
-    if (d->schedule != QR_SCHED_LAUNCH) {
+    // QR_SCHED_AUTO on a graph the fused schedule is not preferred for: the persistent kernel, except on very large
+    // graphs, where its per-claim barriers and atomics cost more than two launches per iteration do (config 4,
+    // 3.7 M edges: 5.09 TB/s launched against 4.69 TB/s persistent on B200)
+    const bool launch_mode = d->schedule == QR_SCHED_LAUNCH || (d->schedule == QR_SCHED_AUTO && d->g->E >= (int64_t(1) << 21));
+    if (!launch_mode) {
         int per_sm = 0;
         QR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<T, VEC, DSEL>,
                                                                     kBlock, 0));

@@ -64,6 +64,9 @@ struct DecodeParams {
     int32_t n_bins;
     const int32_t *chk_order, *slot_var, *var_ptr, *var_slot;
     const int32_t *var_work;   // variable ids sorted by degree (null: every variable has degree var_deg)
+    const CheckBin *var_bins;  // one bin per variable degree over var_work positions, slot lists in vslot_sorted (or null)
+    int32_t n_var_bins;
+    const int32_t *vslot_sorted;
     int64_t N, C, E;
     int32_t var_deg;  // > 0: every variable has this degree (var_slot row of n starts at n * var_deg)
     // workspace
@@ -526,6 +529,143 @@ QR_HD void run_var_fixed(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32
     }
 }
 
+// Variables at positions first, first + stride, ... < count of one degree bin (irregular graphs): the variable id and
+// the DV slot ids of the NEXT item are fetched while the current one is summed, all DV + 1 (+1) row loads of an item
+// are issued back to back -- the same pipeline as the regular case, which the degree-sorted order makes possible.
+template <typename T, int VEC, int DV, int U>
+QR_HD void run_var_bin(const DecodeParams<T> &P, const LaneInfo<VEC> &L, const CheckBin &bin, int32_t first,
+                       int32_t stride, bool masked)
+{
+    // U items per trip (positions k, k + stride, ...): U (DV + 1) independent row loads in flight per thread
+    int32_t cur[U][DV], nxt[U][DV], n_cur[U], n_nxt[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        n_cur[u] = n_nxt[u] = 0;
+        const int32_t k = first + u * stride;
+        if (k < bin.count) {
+            n_cur[u] = P.var_work[bin.chk_begin + k];
+            load_index_row<DV>(P.vslot_sorted, bin.slot_begin + k * DV, cur[u]);
+        }
+    }
+    for (int32_t k0 = first; k0 < bin.count; k0 += U * stride) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int32_t kn = k0 + (U + u) * stride;
+            if (kn < bin.count) {
+                n_nxt[u] = P.var_work[bin.chk_begin + kn];
+                load_index_row<DV>(P.vslot_sorted, bin.slot_begin + kn * DV, nxt[u]);
+            }
+        }
+        if constexpr (U == 2) {
+            // both items' rows loaded before either is summed
+            const bool two = k0 + stride < bin.count;
+            const int32_t lanes = P.lanes;
+            Vec<T, VEC> a0 = ld_row<T, VEC>(P.llr, n_cur[0], lanes, L.l0), a1, m0[DV], m1[DV], o0, o1;
+#pragma unroll
+            for (int i = 0; i < DV; ++i) m0[i] = ld_row<T, VEC>(P.c2v, cur[0][i], lanes, L.l0);
+            if (masked) o0 = ld_row<T, VEC>(P.post, n_cur[0], lanes, L.l0);
+            if (two) {
+                a1 = ld_row<T, VEC>(P.llr, n_cur[1], lanes, L.l0);
+#pragma unroll
+                for (int i = 0; i < DV; ++i) m1[i] = ld_row<T, VEC>(P.c2v, cur[1][i], lanes, L.l0);
+                if (masked) o1 = ld_row<T, VEC>(P.post, n_cur[1], lanes, L.l0);
+            }
+#pragma unroll
+            for (int i = 0; i < DV; ++i) {
+#pragma unroll
+                for (int kk = 0; kk < VEC; ++kk) a0.v[kk] = a0.v[kk] + m0[i].v[kk];
+            }
+            if (masked) {
+#pragma unroll
+                for (int kk = 0; kk < VEC; ++kk)
+                    if (!(L.upd >> kk & 1)) a0.v[kk] = o0.v[kk];
+            }
+            st_row<T, VEC>(P.post, n_cur[0], lanes, L.l0, a0);
+            if (two) {
+#pragma unroll
+                for (int i = 0; i < DV; ++i) {
+#pragma unroll
+                    for (int kk = 0; kk < VEC; ++kk) a1.v[kk] = a1.v[kk] + m1[i].v[kk];
+                }
+                if (masked) {
+#pragma unroll
+                    for (int kk = 0; kk < VEC; ++kk)
+                        if (!(L.upd >> kk & 1)) a1.v[kk] = o1.v[kk];
+                }
+                st_row<T, VEC>(P.post, n_cur[1], lanes, L.l0, a1);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (k0 + u * stride < bin.count) var_item_fixed<T, VEC, DV>(P, L, n_cur[u], cur[u], masked);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            n_cur[u] = n_nxt[u];
+#pragma unroll
+            for (int i = 0; i < DV; ++i) cur[u][i] = nxt[u][i];
+        }
+    }
+}
+
+// a bin of any degree: the slot list in chunks of 8 rows, summed in list order (ascending edge id, decoder.pyx:291-293)
+template <typename T, int VEC>
+QR_HD void run_var_bin_any(const DecodeParams<T> &P, const LaneInfo<VEC> &L, const CheckBin &bin, int32_t first,
+                           int32_t stride, bool masked)
+{
+    const int32_t lanes = P.lanes, deg = bin.degree;
+    for (int32_t k = first; k < bin.count; k += stride) {
+        const int32_t n = P.var_work[bin.chk_begin + k];
+        const int32_t *sl = P.vslot_sorted + bin.slot_begin + k * deg;
+        Vec<T, VEC> acc = ld_row<T, VEC>(P.llr, n, lanes, L.l0), old;
+        if (masked) old = ld_row<T, VEC>(P.post, n, lanes, L.l0);
+        for (int32_t j0 = 0; j0 < deg; j0 += 8) {
+            Vec<T, VEC> m[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j0 + j < deg) m[j] = ld_row<T, VEC>(P.c2v, sl[j0 + j], lanes, L.l0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j0 + j < deg) {
+#pragma unroll
+                    for (int kk = 0; kk < VEC; ++kk) acc.v[kk] = acc.v[kk] + m[j].v[kk];
+                }
+        }
+        if (masked) {
+#pragma unroll
+            for (int kk = 0; kk < VEC; ++kk)
+                if (!(L.upd >> kk & 1)) acc.v[kk] = old.v[kk];
+        }
+        st_row<T, VEC>(P.post, n, lanes, L.l0, acc);
+    }
+}
+
+// positions [p0, p1) of the degree-sorted variable order, rows first, first + stride, ... of that range
+template <typename T, int VEC>
+QR_HD void run_var_binned(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32_t p0, int32_t p1, int32_t first,
+                          int32_t stride)
+{
+    if (!L.upd) return;
+    const bool masked = L.upd != (1u << VEC) - 1u;
+    for (int32_t b = 0; b < P.n_var_bins; ++b) {
+        const CheckBin bin = P.var_bins[b];
+        const int32_t lo = p0 > bin.chk_begin ? p0 : bin.chk_begin;
+        const int32_t hi = p1 < bin.chk_begin + bin.count ? p1 : bin.chk_begin + bin.count;
+        if (lo >= hi) continue;
+        const CheckBin sub{bin.degree, lo, hi - lo, bin.slot_begin + (lo - bin.chk_begin) * bin.degree};
+        switch (bin.degree) {
+        case 1: run_var_bin<T, VEC, 1, 2>(P, L, sub, first, stride, masked); break;
+        case 2: run_var_bin<T, VEC, 2, 2>(P, L, sub, first, stride, masked); break;
+        case 3: run_var_bin<T, VEC, 3, 2>(P, L, sub, first, stride, masked); break;
+        case 4: run_var_bin<T, VEC, 4, 2>(P, L, sub, first, stride, masked); break;
+        case 5: run_var_bin<T, VEC, 5, 2>(P, L, sub, first, stride, masked); break;
+        case 6: run_var_bin<T, VEC, 6, 1>(P, L, sub, first, stride, masked); break;
+        case 8: run_var_bin<T, VEC, 8, 1>(P, L, sub, first, stride, masked); break;
+        default: run_var_bin_any<T, VEC>(P, L, sub, first, stride, masked); break;
+        }
+    }
+}
+
 // All variables n = first, first+stride, ... < n_end for the thread's lanes (decisions already in L).
 // UNROLLED: compile the per-degree unrolled variants for irregular variable degrees (kept out of the kernels
 // specialised for one check degree, whose register allocation they would disturb).
@@ -539,6 +679,12 @@ QR_HD void run_var_range(const DecodeParams<T> &P, const LaneInfo<VEC> &L, int32
     if (P.var_deg == 3) {
         run_var_fixed<T, VEC, 3, U>(P, L, first, stride, n_end, L.upd != (1u << VEC) - 1u);
         return;
+    }
+    if constexpr (UNROLLED) {
+        if (P.var_bins) {          // irregular graph: degree bins over the sorted order (positions 0 .. n_end)
+            run_var_binned<T, VEC>(P, L, 0, n_end, first, stride);
+            return;
+        }
     }
     // irregular variable degrees: positions first, first + stride, ... of the degree-sorted work list.  Within a
     // warp the degree is (almost always) the same, so the unrolled variants issue all their row loads at once

@@ -111,6 +111,8 @@ static int graph_create(const int64_t *h_vid, const int64_t *h_cid, int64_t n_ed
             if ((r = qr::upload(&g->d_bins, g->bins))) return r;
             if (!g->slot_nbr.empty() && (r = qr::upload(&g->d_slot_nbr, g->slot_nbr))) return r;
             if (!g->var_work.empty() && (r = qr::upload(&g->d_var_work, g->var_work))) return r;
+            if (!g->var_bins.empty() && (r = qr::upload(&g->d_var_bins, g->var_bins))) return r;
+            if (!g->vslot_sorted.empty() && (r = qr::upload(&g->d_vslot_sorted, g->vslot_sorted))) return r;
             return QR_OK;
         };
         rc = body();
@@ -129,7 +131,7 @@ void qr_graph_destroy(qr_graph *g)
         cudaGetDevice(&prev);
         cudaSetDevice(g->device);
         cudaFree(g->d_chk_order); cudaFree(g->d_chk_ptr); cudaFree(g->d_slot_var);
-        cudaFree(g->d_var_ptr); cudaFree(g->d_var_slot); cudaFree(g->d_bins); cudaFree(g->d_slot_nbr); cudaFree(g->d_var_work);
+        cudaFree(g->d_var_ptr); cudaFree(g->d_var_slot); cudaFree(g->d_bins); cudaFree(g->d_slot_nbr); cudaFree(g->d_var_work); cudaFree(g->d_var_bins); cudaFree(g->d_vslot_sorted);
         cudaSetDevice(prev);
     }
     delete g;

@@ -102,6 +102,17 @@ inline int build_host_tables(qr_graph &g, const int64_t *vid, const int64_t *cid
         std::stable_sort(g.var_work.begin(), g.var_work.end(),
                          [&](int32_t a, int32_t b) { return vdeg[a] < vdeg[b]; });
     }
+    g.var_bins.clear(); g.vslot_sorted.clear();
+    if (g.var_deg == 0) {
+        g.vslot_sorted.resize(E);
+        int32_t at = 0;
+        for (int64_t pos = 0; pos < N; ++pos) {
+            const int32_t v = g.var_work[pos], d = vdeg[v];
+            if (g.var_bins.empty() || g.var_bins.back().degree != d) g.var_bins.push_back(CheckBin{d, (int32_t)pos, 0, at});
+            g.var_bins.back().count++;
+            for (int j = 0; j < d; ++j) g.vslot_sorted[at++] = g.var_slot[g.var_ptr[v] + j];
+        }
+    }
     // neighbour table of the fused schedule: what a check needs to rebuild post[v] = llr[v] + sum c2v
     // (decoder.pyx:291-293) of each of its variables without a stored posterior (record layout: Nbr4,
     // qr_decode_fused.cuh)

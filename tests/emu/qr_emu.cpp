@@ -52,6 +52,8 @@ static int emu_decode_t(const qr_graph &g, int lanes, bool generic, const void *
     P.chk_order = g.chk_order.data(); P.slot_var = g.slot_var.data();
     P.var_ptr = g.var_ptr.data(); P.var_slot = g.var_slot.data();
     P.var_work = g.var_work.empty() ? nullptr : g.var_work.data();
+    P.var_bins = g.var_bins.empty() ? nullptr : g.var_bins.data(); P.n_var_bins = (int32_t)g.var_bins.size();
+    P.vslot_sorted = g.vslot_sorted.empty() ? nullptr : g.vslot_sorted.data();
     P.N = g.N; P.C = g.C; P.E = g.E; P.lanes = lanes; P.var_deg = g.var_deg;
     P.c2v = c2v.data(); P.post = postw.data(); P.llr = llrw.data(); P.synd = syndw.data();
     P.st[0] = st.data(); P.st[1] = st.data() + lanes;
@@ -136,6 +138,7 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     P.chk_order = g.chk_order.data(); P.slot_var = g.slot_var.data();
     P.var_ptr = g.var_ptr.data(); P.var_slot = g.var_slot.data();
     P.var_work = g.var_work.empty() ? nullptr : g.var_work.data();
+    P.var_bins = nullptr; P.n_var_bins = 0; P.vslot_sorted = nullptr;
     P.N = g.N; P.C = g.C; P.E = g.E; P.lanes = lanes; P.var_deg = g.var_deg;
     P.c2v = nullptr; P.post = nullptr; P.llr = llrw.data(); P.synd = syndw.data();
     P.st[0] = st.data(); P.st[1] = nullptr;

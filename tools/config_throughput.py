@@ -64,11 +64,15 @@ def main():
     ap.add_argument("--lanes3", default="256", help="comma list of resident-frame counts tried for config 3")
     ap.add_argument("--lanes4", default="128", help="the same for config 4")
     ap.add_argument("--schedule", type=int, default=3)
+    ap.add_argument("--only", type=int, default=0, help="3 or 4: run only that configuration")
     a = ap.parse_args()
     SCHEDULE = a.schedule
     vid, cid = codes.irregular_ldpc(131070, 104856, [3, 8], [0.9, 0.1], seed=3)
     cfg = np.zeros(8, dtype=np.uint8); cfg[1::2] = 1
-    run("3: irregular n=131070 R=0.2 8-PAM", vid, cid, 3, 3.0, cfg, a.frames3, 100, [int(v) for v in a.lanes3.split(",")])
+    if a.only in (0, 3):
+        run("3: irregular n=131070 R=0.2 8-PAM", vid, cid, 3, 3.0, cfg, a.frames3, 100, [int(v) for v in a.lanes3.split(",")])
+    if a.only == 3:
+        return
     vid, cid = codes.irregular_ldpc(1 << 20, 943718, [3, 4, 10], [0.8, 0.15, 0.05], seed=4)
     run("4: irregular n=2^20 R=0.1 2-PAM", vid, cid, 1, -12.0, np.array([0, 1], dtype=np.uint8), a.frames4, 60, [int(v) for v in a.lanes4.split(",")])
 
