@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../qam-reconciliation_b200/csrc/qr_common.h"
@@ -172,12 +173,37 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     ctrl[CTRL_REMAINING] = (int32_t)frames;
     ctrl[CTRL_MINFIN] = 0x7fffffff;
     int64_t shipped_from_post = 0, completed = 0;
+    // float mode on a (3,6)-regular graph: the lean item with premultiplied-offset records, as on the device
+    std::vector<NbrL> lean;
+    if constexpr (std::is_same<T, float>::value) {
+        if (g.var_deg == 3 && g.bins.size() == 1 && g.bins[0].degree == 6) {
+            lean.resize(g.E);
+            for (int64_t e = 0; e < g.E; ++e) lean[e] = make_lean_record(F.nbr[e], tl);
+            F.nbr_lean = lean.data();
+        }
+    }
     auto sweep = [&](int tile, int cur) {
         const TileView<T> V = tile_view(F, cur, tile);
         for (int tx = 0; tx < tl / VEC; ++tx) {
             const LaneInfo<VEC> L = load_tile_lanes<T, VEC>(F, (tile * tl) / VEC + tx, tile_minfin[tile]);
             if (!L.active) continue;
             uint32_t bad = 0;
+            if constexpr (std::is_same<T, float>::value) {
+                if (!lean.empty()) {
+                    const int32_t lt4 = tx * VEC * 4;
+                    for (int32_t ci = 0; ci < g.C; ++ci) {
+                        const char *llr_t = reinterpret_cast<const char *>(V.llr) + lt4;
+                        const char *cold_t = reinterpret_cast<const char *>(V.c_old) + lt4;
+                        char *cnew_t = reinterpret_cast<char *>(V.c_new) + lt4;
+                        char *post_t = reinterpret_cast<char *>(V.post) + lt4;
+                        if (L.fresh) bad |= fused_item_lean<6, true>(llr_t, cold_t, cnew_t, post_t, V.synd + tx * VEC, lean.data(), ci, 6 * ci, tl, L.fresh, L.wpost, L.active, 0, 0, 0);
+                        else bad |= fused_item_lean<6, false>(llr_t, cold_t, cnew_t, post_t, V.synd + tx * VEC, lean.data(), ci, 6 * ci, tl, 0u, L.wpost, L.active, 0, 0, 0);
+                    }
+                    for (int k = 0; k < VEC; ++k)
+                        if (bad >> k & 1) P.unsat[0][L.l0 + k] = 1;
+                    continue;
+                }
+            }
             for (const CheckBin &bin : g.bins)
                 for (int32_t t = 0; t < 3; ++t)
                     bad |= run_fused_bin_any<T, VEC>(V, F.nbr, L, tx * VEC, bin, t, 3, 0, 0);

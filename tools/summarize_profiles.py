@@ -13,7 +13,7 @@ from collections import OrderedDict
 
 KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
@@ -52,6 +52,9 @@ def kernels(rep, dst):
             t = float(r[hdr.index('gpu__time_duration.sum')])
             tu = {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1}[units[hdr.index('gpu__time_duration.sum')]]
             fh.write(f"{'derived: DRAM traffic (read+write) / duration':82s} {(rd + wr) * scale / (t * tu) / 1e9:22.1f} GB/s\n")
+            if "lts__t_bytes.sum" in hdr:
+                lb = float(r[hdr.index("lts__t_bytes.sum")]) * {"Tbyte": 1e12, "Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[units[hdr.index("lts__t_bytes.sum")]]
+                fh.write(f"{'derived: L2 traffic (lts__t_bytes) / duration':82s} {lb / (t * tu) / 1e9:22.1f} GB/s\n")
 
 
 def launches(src, dst):
