@@ -246,7 +246,8 @@ def _noop(_):
 def workload_config(a, n_sets=2):
     """The `config` object of the JSON line: the workload both arms are quoted on."""
     B, S = a.frames, a.n // BPS
-    return {"workload": workload_name(a.n, a.snr), "frames_per_gpu_per_step": B, "demap": a.demap,
+    return {"workload": workload_name(a.n, a.snr), "frames_per_gpu_per_step": B,
+            "demap": a.demap + (" (fp32 grade: QR_DEMAP_FAST | QR_DEMAP_F32GRADE)" if a.demap == "fast" and a.precision == "fp32" else ""),
             "decoder_lanes": a.lanes or 512, "schedule": {0: "persistent", 1: "launch", 2: "fused", 3: "auto"}[a.schedule],
             "l2_policy": f"{n_sets} alternating input sets of {B * S * 16 / 1e9:.1f} GB each (>> 126 MB L2)"}
 
@@ -390,8 +391,29 @@ class Workload:
         d2h = self.B * (1 + 4 + 4) + outs["post"].numel() * outs["post"].element_size()
         return el, h2d, d2h
 
-    def roofline(self, k_ms, fi, kname, traffic=None):
+    def e2e_compact_leg(self, steps, warmup, barrier):
+        """The same pass over the compact wire format (qr_reconcile_host_compact): float32 samples and byte symbols in,
+        hard decisions packed 8 per byte out.  NOT the reference's types: reported under its own key."""
+        torch = self.torch
+        hy = [y.float().cpu().pin_memory() for y in self.ys]
+        hx = [x.to(torch.uint8).cpu().pin_memory() for x in self.xs]
+        outs = dict(success=torch.empty(self.B, dtype=torch.uint8).pin_memory(),
+                    iters=torch.empty(self.B, dtype=torch.int32).pin_memory(),
+                    bit_errors=torch.empty(self.B, dtype=torch.int32).pin_memory(),
+                    decisions=torch.empty((self.B, (self.n + 7) // 8), dtype=torch.uint8).pin_memory())
+        for i in range(min(warmup, 2)):
+            self.rec.run_host_compact(hy[i % self.n_sets], hx[i % self.n_sets], self.maxiter, self.K, outs)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            self.rec.run_host_compact(hy[i % self.n_sets], hx[i % self.n_sets], self.maxiter, self.K, outs)
+        barrier()
+        el = time.perf_counter() - t0
+        return el, self.B * self.S * 5, self.B * (1 + 4 + 4) + outs["decisions"].numel()
+
+    def roofline(self, k_ms, fi, kname, ent=None):
         peak, peak_src = peaks()
+        traffic = ent["dram_bytes_per_launch"] if ent else None
         achieved = fi * self.bytes_per_frame_iter / (k_ms / 1e3) / 1e9
         r = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -402,6 +424,13 @@ class Workload:
             # what the HBM really carried (ncu dram__bytes of the same launch) over the live launch time
             r["dram_GBps"] = traffic / (k_ms / 1e3) / 1e9
             r["dram_frac"] = r["dram_GBps"] / peak
+            if ent.get("l2_bytes_per_launch"):
+                # the level that actually bounds the fused kernel: L2 throughput (lts__t_bytes of the same capture) against
+                # the builder-measured L2 gather bandwidth (tools/membench.cu, profiles/r2_membench.txt)
+                r["l2_GBps"] = ent["l2_bytes_per_launch"] / (k_ms / 1e3) / 1e9
+                r["l2_peak_GBps"] = ent.get("l2_peak_GBps")
+                r["l2_frac"] = r["l2_GBps"] / ent["l2_peak_GBps"] if ent.get("l2_peak_GBps") else None
+            r["traffic_source"] = ent.get("source")
         return r
 
 
@@ -419,7 +448,7 @@ def lookup_traffic(n, B, maxiter, precision, schedule, lanes, fi):
             sched = {"persistent": 0, "launch": 1, "fused": 2}[c["schedule"]]
             if (c["n"], c["frames"], c["max_iterations"], c["precision"], sched, c["lanes"]) == \
                     (n, B, maxiter, precision, schedule, lanes) and fi == ent.get("frame_iterations", B * maxiter):
-                best = ent["dram_bytes_per_launch"]        # later rounds override earlier ones
+                best = ent                                 # later rounds override earlier ones
     return best
 
 
@@ -495,6 +524,15 @@ def ours(a):
                "api": "qr_reconcile_host: host y (f64) + tx symbols (i64) in; success, iterations, bit errors and "
                       "final LLRs out; pinned host memory"}
 
+    # ---- the same through the compact wire format (an extension, own key: not the reference's array types)
+    e2e_compact = None
+    if not a.no_e2e:
+        el, h2d, d2h = wl.e2e_compact_leg(a.steps, a.warmup, barrier)
+        e2e_compact = {"value": total_frames / max_over_ranks(el), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h,
+                       "api": "qr_reconcile_host_compact: host y (f32) + tx symbols (u8) in; success, iterations, bit errors "
+                              "and packed hard decisions out; pinned host memory"}
+
     # ---- supplementary operating points (N = 1 only: they are reported, not scaled)
     points = None
     if world == 1 and not a.no_extras and n == N_CODE:
@@ -515,9 +553,9 @@ def ours(a):
             "info_gbit_per_s": value * K / 1e9,
             "avg_iterations": fi / B, "ber": cnt[0] / max(1, cnt[4] * K), "fer": cnt[1] / max(1, cnt[4]),
             "counters_all_reduced_inside_timed_region": True,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            # per step: front end, syndrome, demapper, batch init, persistent decoder, error count
-            "gpu_launches": 6 * a.steps * world, "clocks": clocks}
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_compact": e2e_compact,
+            # per step: k_front_end, k_eval_syndrome, k_demap32, k_init_batch, k_init_fused, k_fused, k_count_errors
+            "gpu_launches": 7 * a.steps * world, "clocks": clocks}
     if points is not None:
         line["operating_points"] = points
     print(json.dumps(line))

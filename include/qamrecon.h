@@ -241,6 +241,17 @@ int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, int demap_mod
                       void *h_post, int post_dtype, uint8_t *h_word, int32_t *h_bit_errors,
                       void *stream);
 
+/* The same pass over a COMPACT WIRE FORMAT (an extension: the reference's arrays are float64 / int64): channel
+ * outputs as float32, Alice's symbols as bytes (alphabets of at most 256 points), and instead of the final LLRs the
+ * decoder's hard decisions (decoder.pyx:244: bit = lappr < 0) packed 8 per byte, bit (i & 7) of byte i >> 3 of a
+ * frame's row of ceil(N / 8) bytes.  5 bytes per symbol in and N / 8 bytes per frame out instead of 16 and 4 N:
+ * what a deployment whose host link is the limit would ship (bench.py reports it as `e2e_compact`).  Widening and
+ * packing happen on the device; everything in between is the chain of qr_reconcile_host, unchanged. */
+int qr_reconcile_host_compact(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha,
+                              const float *h_y32, const uint8_t *h_tx8, int64_t frames, int32_t max_iterations,
+                              int64_t k_info, uint8_t *h_success, int32_t *h_iters, uint8_t *h_decisions_packed,
+                              int32_t *h_bit_errors, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

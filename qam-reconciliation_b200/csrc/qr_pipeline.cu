@@ -18,6 +18,32 @@
 
 namespace {
 
+// compact wire format: float samples / byte symbols widened on the device, hard decisions packed 8 per byte
+__global__ void k_widen(const float *__restrict__ y32, const uint8_t *__restrict__ tx8, int64_t n, double *__restrict__ y,
+                        long long *__restrict__ tx)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        y[i] = (double)y32[i];
+        tx[i] = (long long)tx8[i];
+    }
+}
+
+// bit (i & 7) of byte i >> 3 of a frame's row = (posterior[i] < 0), the hard decision of decoder.pyx:244
+template <typename T>
+__global__ void k_pack_decisions(const T *__restrict__ post, int64_t frames, int64_t N, int64_t row_bytes,
+                                 uint8_t *__restrict__ packed)
+{
+    const int64_t total = frames * row_bytes;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = j / row_bytes, b = j - f * row_bytes;
+        const T *p = post + f * N + b * 8;
+        uint32_t v = 0;
+        for (int k = 0; k < 8; ++k)
+            if (b * 8 + k < N && p[k] < (T)0) v |= 1u << k;
+        packed[j] = (uint8_t)v;
+    }
+}
+
 struct Carver {
     char *base;
     size_t off = 0;
@@ -38,11 +64,16 @@ struct Buffers {
     uint8_t *word, *synd, *success;
     void *llr, *post;
     int32_t *iters, *errors;
+    float *y32;          // compact wire format only
+    uint8_t *tx8, *packed;
 };
 
-Buffers carve(Carver &c, int64_t frames, int64_t S, int64_t N, int64_t C, size_t wl, size_t wp)
+Buffers carve(Carver &c, int64_t frames, int64_t S, int64_t N, int64_t C, size_t wl, size_t wp, bool compact = false)
 {
     Buffers b;
+    b.y32 = compact ? c.take<float>(frames * S) : nullptr;
+    b.tx8 = compact ? c.take<uint8_t>(frames * S) : nullptr;
+    b.packed = compact ? c.take<uint8_t>(frames * ((N + 7) / 8)) : nullptr;
     b.y = c.take<double>(frames * S);
     b.n_hat = c.take<double>(frames * S);
     b.tx = c.take<int64_t>(frames * S);
@@ -135,12 +166,42 @@ extern "C" int qr_reconcile_device(qr_decoder *d, const qr_mapper *m, int mode, 
                      synd, llr, llr_dtype, d_success, d_iters, post, post_dtype, d_bit_errors, st);
 }
 
+static int reconcile_host_impl(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha,
+                               const double *h_y, const int64_t *h_tx_index, const float *h_y32, const uint8_t *h_tx8,
+                               int64_t frames, int32_t max_iterations, int64_t k_info, uint8_t *h_success,
+                               int32_t *h_iters, void *h_post, int post_dtype, uint8_t *h_word, uint8_t *h_packed,
+                               int32_t *h_bit_errors, void *stream_);
+
 extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha,
                                  const double *h_y, const int64_t *h_tx_index, int64_t frames,
                                  int32_t max_iterations, int64_t k_info, uint8_t *h_success,
                                  int32_t *h_iters, void *h_post, int post_dtype, uint8_t *h_word,
                                  int32_t *h_bit_errors, void *stream_)
 {
+    if (frames > 0 && (!h_y || !h_tx_index)) return qr::fail(QR_ERR_INVALID, "null input array");
+    return reconcile_host_impl(d, m, mode, demap_mode, alpha, h_y, h_tx_index, nullptr, nullptr, frames, max_iterations,
+                               k_info, h_success, h_iters, h_post, post_dtype, h_word, nullptr, h_bit_errors, stream_);
+}
+
+extern "C" int qr_reconcile_host_compact(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha,
+                                         const float *h_y32, const uint8_t *h_tx8, int64_t frames,
+                                         int32_t max_iterations, int64_t k_info, uint8_t *h_success, int32_t *h_iters,
+                                         uint8_t *h_decisions_packed, int32_t *h_bit_errors, void *stream_)
+{
+    if (frames > 0 && (!h_y32 || !h_tx8)) return qr::fail(QR_ERR_INVALID, "null input array");
+    if (m && m->order > 256) return qr::fail(QR_ERR_INVALID, "byte symbols need an alphabet of at most 256 points");
+    return reconcile_host_impl(d, m, mode, demap_mode, alpha, nullptr, nullptr, h_y32, h_tx8, frames, max_iterations,
+                               k_info, h_success, h_iters, nullptr, QR_F32, nullptr, h_decisions_packed, h_bit_errors,
+                               stream_);
+}
+
+static int reconcile_host_impl(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha,
+                               const double *h_y, const int64_t *h_tx_index, const float *h_y32, const uint8_t *h_tx8,
+                               int64_t frames, int32_t max_iterations, int64_t k_info, uint8_t *h_success,
+                               int32_t *h_iters, void *h_post, int post_dtype, uint8_t *h_word, uint8_t *h_packed,
+                               int32_t *h_bit_errors, void *stream_)
+{
+    const bool compact = h_y32 != nullptr;
     if (!d || !m) return qr::fail(QR_ERR_INVALID, "null handle");
     if (mode < 0 || mode > 2) return qr::fail(QR_ERR_INVALID, "reconciliation mode must be 0, 1 or 2");
     if (frames < 0) return qr::fail(QR_ERR_INVALID, "bad frame count");
@@ -151,12 +212,12 @@ extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, in
     if (k_info < 0 || k_info > N) return qr::fail(QR_ERR_INVALID, "bad information length");
     if (h_post && post_dtype != QR_F32 && post_dtype != QR_F64) return qr::fail(QR_ERR_INVALID, "bad dtype");
     if (frames == 0) return QR_OK;
-    if (!h_y || !h_tx_index) return qr::fail(QR_ERR_INVALID, "null input array");
     const int64_t S = N / m->bps;
     const int llr_dtype = d->precision == QR_F64 ? QR_F64 : QR_F32;
     const size_t wl = llr_dtype == QR_F64 ? 8 : 4;
     if (!h_post) post_dtype = llr_dtype;
     const size_t wp = post_dtype == QR_F64 ? 8 : 4;
+    const int64_t row_bytes = (N + 7) / 8;
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     qr::DeviceGuard guard(d->device);
 
@@ -193,7 +254,7 @@ extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, in
     }
 
     Carver sizing(nullptr);
-    for (int s = 0; s < n_sets; ++s) carve(sizing, chunk, S, N, C, wl, wp);
+    for (int s = 0; s < n_sets; ++s) carve(sizing, chunk, S, N, C, wl, wp, compact);
     const size_t need = sizing.off + 256;
     if (need > d->pipe_cap) {
         QR_CUDA_CHECK(cudaDeviceSynchronize());
@@ -205,7 +266,7 @@ extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, in
     }
     Carver carver(d->pipe_buf);
     Buffers sets[2];
-    for (int s = 0; s < n_sets; ++s) sets[s] = carve(carver, chunk, S, N, C, wl, wp);
+    for (int s = 0; s < n_sets; ++s) sets[s] = carve(carver, chunk, S, N, C, wl, wp, compact);
 
     // work queued on the caller's stream before this call must precede our copies
     QR_CUDA_CHECK(cudaEventRecord(d->ev_start, st));
@@ -218,19 +279,35 @@ extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, in
         const int64_t f0 = cuts[c], nf = cuts[c + 1] - cuts[c];
         // stage 1: inputs of chunk c (the set is free once the kernels of chunk c-2 are done)
         if (c >= n_sets) QR_CUDA_CHECK(cudaStreamWaitEvent(d->s_in, d->ev_compute[s], 0));
-        QR_CUDA_CHECK(cudaMemcpyAsync(b.y, h_y + f0 * S, nf * S * sizeof(double), cudaMemcpyHostToDevice, d->s_in));
-        QR_CUDA_CHECK(cudaMemcpyAsync(b.tx, h_tx_index + f0 * S, nf * S * sizeof(int64_t), cudaMemcpyHostToDevice, d->s_in));
+        if (compact) {
+            QR_CUDA_CHECK(cudaMemcpyAsync(b.y32, h_y32 + f0 * S, nf * S * sizeof(float), cudaMemcpyHostToDevice, d->s_in));
+            QR_CUDA_CHECK(cudaMemcpyAsync(b.tx8, h_tx8 + f0 * S, nf * S, cudaMemcpyHostToDevice, d->s_in));
+        } else {
+            QR_CUDA_CHECK(cudaMemcpyAsync(b.y, h_y + f0 * S, nf * S * sizeof(double), cudaMemcpyHostToDevice, d->s_in));
+            QR_CUDA_CHECK(cudaMemcpyAsync(b.tx, h_tx_index + f0 * S, nf * S * sizeof(int64_t), cudaMemcpyHostToDevice, d->s_in));
+        }
         QR_CUDA_CHECK(cudaEventRecord(d->ev_in[s], d->s_in));
         // stage 2: kernels (outputs of the set are free once chunk c-2 has been copied out)
         QR_CUDA_CHECK(cudaStreamWaitEvent(st, d->ev_in[s], 0));
         if (c >= n_sets) QR_CUDA_CHECK(cudaStreamWaitEvent(st, d->ev_out[s], 0));
+        if (compact) {
+            k_widen<<<(unsigned)std::min<int64_t>((nf * S + 255) / 256, 148 * 16), 256, 0, st>>>(
+                b.y32, b.tx8, nf * S, b.y, reinterpret_cast<long long *>(b.tx));
+            QR_CUDA_CHECK(cudaGetLastError());
+        }
         int rc = run_chain(d, m, mode, demap_mode, alpha, b.y, b.tx, nf, S, max_iterations, k_info, b.n_hat, b.word,
                            b.synd, b.llr, llr_dtype, b.success, b.iters, b.post, post_dtype,
-                           h_bit_errors ? b.errors : nullptr, st);
+                           h_bit_errors ? b.errors : nullptr, st);   // (b.post: also what the packed decisions are taken from)
         if (rc) {
             // copies of this and earlier chunks may still be in flight into / out of caller memory
             cudaStreamSynchronize(d->s_in); cudaStreamSynchronize(st); cudaStreamSynchronize(d->s_out);
             return rc;
+        }
+        if (h_packed) {
+            const unsigned pg = (unsigned)std::min<int64_t>((nf * row_bytes + 255) / 256, 148 * 16);
+            if (post_dtype == QR_F64) k_pack_decisions<double><<<pg, 256, 0, st>>>(static_cast<const double *>(b.post), nf, N, row_bytes, b.packed);
+            else k_pack_decisions<float><<<pg, 256, 0, st>>>(static_cast<const float *>(b.post), nf, N, row_bytes, b.packed);
+            QR_CUDA_CHECK(cudaGetLastError());
         }
         QR_CUDA_CHECK(cudaEventRecord(d->ev_compute[s], st));
         // stage 3: results of chunk c
@@ -243,6 +320,8 @@ extern "C" int qr_reconcile_host(qr_decoder *d, const qr_mapper *m, int mode, in
             QR_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(h_post) + (size_t)f0 * N * wp, b.post, (size_t)nf * N * wp,
                                           cudaMemcpyDeviceToHost, d->s_out));
         if (h_word) QR_CUDA_CHECK(cudaMemcpyAsync(h_word + f0 * N, b.word, nf * N, cudaMemcpyDeviceToHost, d->s_out));
+        if (h_packed)
+            QR_CUDA_CHECK(cudaMemcpyAsync(h_packed + f0 * row_bytes, b.packed, nf * row_bytes, cudaMemcpyDeviceToHost, d->s_out));
         QR_CUDA_CHECK(cudaEventRecord(d->ev_out[s], d->s_out));
     }
     QR_CUDA_CHECK(cudaStreamSynchronize(d->s_out));

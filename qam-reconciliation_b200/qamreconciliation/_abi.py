@@ -63,6 +63,8 @@ SIGNATURES = {
     "qr_information_sums": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp]),
     "qr_reconcile_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f64, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp,
                                       C.c_int, _vp, _vp, _vp, _vp]),
+    "qr_reconcile_host_compact": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f64, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp,
+                                            _vp, _vp]),
     "qr_reconcile_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f64, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp,
                                     C.c_int, _vp, _vp, _vp]),
 }

@@ -109,3 +109,24 @@ class Reconciler:
             word.data_ptr() if word is not None else None, out["bit_errors"].data_ptr(), stream()))
         self.nm.check_indices()      # (the call above has synchronised: this costs one 4-byte copy)
         return out
+
+    def run_host_compact(self, y32, x8, max_iterations, k_info, out):
+        """Compact wire format through qr_reconcile_host_compact: y32 float32 [B, S], x8 uint8 [B, S] CPU tensors in;
+        `out`: success uint8[B], iters int32[B], bit_errors int32[B], decisions uint8[B, ceil(N / 8)] (hard decisions
+        of the final LLRs, 8 per byte)."""
+        for name, t, dt in (("y32", y32, torch.float32), ("x8", x8, torch.uint8)):
+            if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != dt or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous CPU tensor of dtype {dt}")
+        if y32.dim() != 2 or y32.shape[1] != self.S or x8.shape != y32.shape:
+            raise ValueError(f"y32 and x8 must both have shape [frames, {self.S}]")
+        B = y32.shape[0]
+        dec = out["decisions"]
+        if dec.is_cuda or dec.dtype != torch.uint8 or tuple(dec.shape) != (B, (self.N + 7) // 8) or not dec.is_contiguous():
+            raise ValueError(f"out['decisions'] must be a contiguous uint8 CPU tensor of shape {(B, (self.N + 7) // 8)}")
+        h = self.dec._handle(self.prec_code, self.lanes, self.schedule)
+        _abi.check(_abi.lib().qr_reconcile_host_compact(
+            h, self.nm._h, self.mode, self.demap_code, self.alpha, y32.data_ptr(), x8.data_ptr(), B,
+            int(max_iterations), int(k_info), out["success"].data_ptr(), out["iters"].data_ptr(), dec.data_ptr(),
+            out["bit_errors"].data_ptr(), stream()))
+        self.nm.check_indices()
+        return out
