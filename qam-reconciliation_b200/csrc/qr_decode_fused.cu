@@ -286,30 +286,55 @@ __device__ __forceinline__ void fused_initial_fill(const FusedParams<T> &F)
 // ---------------------------------------------------------------------------------------------
 // One claim of F(tile, round): checks [c0, c1) of the tile for the warp.
 template <typename T, int VEC, int DSEL, int VDEG>
-__device__ __forceinline__ uint32_t fused_claim(const FusedParams<T> &F, const TileView<T> &V, const LaneInfo<VEC> &L,
-                                                int32_t c0, int32_t c1, int32_t tx, int32_t tyw, int32_t wy,
-                                                uint64_t pol_ld, uint64_t pol_st, uint64_t pol_post = 0)
+__device__ __forceinline__ uint32_t fused_claim(const FusedParams<T> &F, int32_t tile, int32_t round, uint32_t flags,
+                                                int32_t c0, int32_t c1, int32_t lid)
 {
+    // Everything the rows need is derived HERE from (tile, round, flags) and the constant bank: nothing of it is
+    // live across the passes of a claim, where the item wants every register (spilled control state costs L2
+    // bandwidth -- local memory is write-through -- which is what bounds this kernel).
+    if constexpr (std::is_same<T, float>::value && VEC == 4 && DSEL == 6 && VDEG == 3) {
+        // (this instantiation is only launched with lean records: the generic item is not compiled into it)
+        // check-regular graph: internal check ci has CSR slots [6 ci, 6 ci + 6)
+        int32_t tl = F.tl;
+        asm volatile("" : "+r"(tl));          // opaque: no tile pointer arithmetic is hoisted out of the pass loop and spilled
+        const int32_t bx = tl >> 2, tx = lid % bx, tyw = lid / bx;
+        uint32_t active = 0, fresh = 0, wpost = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t f = flags >> (8 * k);
+            active |= (f & 1u) << k;
+            fresh |= ((f >> 1) & 1u) << k;
+            wpost |= ((f >> 2) & 1u) << k;
+        }
+        const int32_t ci = c0 + tyw;          // (a pass is one row per thread: c1 - c0 <= 32 / bx)
+        if (!active || ci >= c1) return 0;
+        const int cur = round & 1;
+        const NbrL *rec = static_cast<const NbrL *>(F.nbr_lean);
+        const int64_t tile_b = (int64_t)tile * tl * 4;
+        const char *llr_t = reinterpret_cast<const char *>(F.P.llr) + tile_b * F.P.N + tx * 16;
+        const char *cold_t = reinterpret_cast<const char *>(F.c2v[cur]) + tile_b * F.P.E + tx * 16;
+        char *cnew_t = reinterpret_cast<char *>(F.c2v[cur ^ 1]) + tile_b * F.P.E + tx * 16;
+        char *post_t = F.post ? reinterpret_cast<char *>(F.post) + tile_b * F.P.N + tx * 16 : nullptr;
+        const uint8_t *synd_t = F.P.synd + (int64_t)tile * tl * F.P.C + tx * 4;
+        if (fresh) return fused_item_lean<6, true>(llr_t, cold_t, cnew_t, post_t, synd_t, rec, ci, 6 * ci, tl, fresh, wpost, active, F.hints >= 1);
+        return fused_item_lean<6, false>(llr_t, cold_t, cnew_t, post_t, synd_t, rec, ci, 6 * ci, tl, 0u, wpost, active, F.hints >= 1);
+    } else {
+    const int32_t bx = F.tl / VEC, tx = lid % bx, tyw = lid / bx, wy = 32 / bx;
+    LaneInfo<VEC> L;
+    L.l0 = tile * F.tl + tx * VEC;
+    L.active = L.fresh = L.wpost = L.fin_ok = L.fin_fail = L.upd = 0;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        const uint32_t f = flags >> (8 * k);
+        L.active |= (f & 1u) << k;
+        L.fresh |= ((f >> 1) & 1u) << k;
+        L.wpost |= ((f >> 2) & 1u) << k;
+    }
+    if (!L.active) return 0;
+    const TileView<T> V = tile_view(F, round & 1, tile);
+    const uint64_t pol_ld = l2_policy(F.hints == 2 ? 2 : 0), pol_st = l2_policy(F.hints >= 1 ? 1 : 0);
     const DecodeParams<T> &P = F.P;
     uint32_t bad = 0;
-    if constexpr (std::is_same<T, float>::value && VEC == 4 && DSEL == 6 && VDEG == 3) {
-        {
-            // (this instantiation is only launched with lean records: the generic item is not compiled into it)
-            // check-regular graph: internal check ci has CSR slots [6 ci, 6 ci + 6)
-            const NbrL *rec = static_cast<const NbrL *>(F.nbr_lean);
-            const int32_t lt4 = tx * VEC * 4;
-            const char *llr_t = reinterpret_cast<const char *>(V.llr) + lt4;
-            const char *cold_t = reinterpret_cast<const char *>(V.c_old) + lt4;
-            char *cnew_t = reinterpret_cast<char *>(V.c_new) + lt4;
-            char *post_t = reinterpret_cast<char *>(V.post) + lt4;
-            const uint8_t *synd_t = V.synd + tx * VEC;
-            for (int32_t ci = c0 + tyw; ci < c1; ci += wy) {
-                if (L.fresh) bad |= fused_item_lean<6, true>(llr_t, cold_t, cnew_t, post_t, synd_t, rec, ci, 6 * ci, V.tl, L.fresh, L.wpost, L.active, pol_ld, pol_st, pol_post);
-                else bad |= fused_item_lean<6, false>(llr_t, cold_t, cnew_t, post_t, synd_t, rec, ci, 6 * ci, V.tl, 0u, L.wpost, L.active, pol_ld, pol_st, pol_post);
-            }
-            return bad;
-        }
-    } else
     for (int32_t b = 0; b < P.n_bins; ++b) {
         const CheckBin bin = P.bins[b];
         const int32_t lo = max(c0, bin.chk_begin), hi = min(c1, bin.chk_begin + bin.count);
@@ -319,6 +344,7 @@ __device__ __forceinline__ uint32_t fused_claim(const FusedParams<T> &F, const T
         else bad |= run_fused_bin_any<T, VEC>(V, F.nbr, L, tx * VEC, sub, tyw, wy, pol_ld, pol_st);
     }
     return bad;
+    }
 }
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
@@ -342,6 +368,7 @@ struct WarpCtl {
     int32_t cnt_tile, cnt_round, cnt_val;   // count issued, result arrives during the next claim
     uint32_t flags, n_flags;          // lane flag bytes of this thread's lanes: kept per LANE below, not here
     int32_t n_have_flags;
+    uint32_t cpt;                     // claims per tile sweep
 };
 
 // (cold paths out of line; F is a __grid_constant__ kernel parameter, so the reference is a pointer into the
@@ -384,12 +411,14 @@ __global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __gri
     // lock step: "all lanes write the same value" races with the next update of the same field.)
     volatile WarpCtl &w = s_ctl[threadIdx.x >> 5];
     const int32_t lid = threadIdx.x & 31;
-    const uint32_t cpt = (uint32_t)(((int32_t)P.C + (32 / (F.tl / VEC)) * F.rows_per_claim - 1) / ((32 / (F.tl / VEC)) * F.rows_per_claim));
+    if (lid == 0)
+        w.cpt = (uint32_t)(((int32_t)P.C + (32 / (F.tl / VEC)) * F.rows_per_claim - 1) / ((32 / (F.tl / VEC)) * F.rows_per_claim));
+    __syncwarp();
     const int32_t frames = (int32_t)P.frames;
 
     // claim id -> coordinates (lane 0)
-    auto set_coord0 = [&](unsigned long long q, bool next) {
-        const uint32_t q32 = (uint32_t)q, per_round = cpt * (uint32_t)F.tiles;
+    auto set_coord0 = [&](uint32_t q, bool next) {
+        const uint32_t cpt = w.cpt, q32 = (uint32_t)q, per_round = cpt * (uint32_t)F.tiles;
         const uint32_t round = q32 / per_round, rem = q32 - round * per_round, tile = rem / cpt;
         if (next) { w.n_round = (int32_t)round; w.n_tile = (int32_t)tile; w.n_chunk = (int32_t)(rem - tile * cpt); }
         else { w.round = (int32_t)round; w.tile = (int32_t)tile; w.chunk = (int32_t)(rem - tile * cpt); }
@@ -411,7 +440,7 @@ __global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __gri
         __syncwarp();
         const int32_t ct = w.cnt_tile, cr = w.cnt_round;
         if (ct < 0) return;
-        const bool last = (uint32_t)(w.cnt_val + 1) == cpt * (uint32_t)(cr + 1);
+        const bool last = (uint32_t)(w.cnt_val + 1) == w.cpt * (uint32_t)(cr + 1);
         __syncwarp();
         if (lid == 0) w.cnt_tile = -1;
         __syncwarp();
@@ -464,7 +493,7 @@ __global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __gri
 
     if (lid == 0) {
         const unsigned long long q = atomicAdd(reinterpret_cast<unsigned long long *>(P.work), 1ULL);
-        set_coord0(q, false);
+        set_coord0((uint32_t)q, false);
         w.ticket = (uint32_t)atomicAdd(&P.ctrl[CTRL_PP_HEAD], 1);
         w.sig_tile = -1; w.cnt_tile = -1;
         load_pre0(w.tile);
@@ -500,59 +529,45 @@ __global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __gri
             continue;                                              // (re-check the slot with the fresh loads)
         }
         if (!have_flags) flags = load_flags(w.tile);
-        unsigned long long nq = 0, p_slot = 0, p_bk = 0;
-        int32_t p_done = 0, p_ppd = 0;
-        if (lid == 0) nq = atomicAdd(reinterpret_cast<unsigned long long *>(P.work), 1ULL);   // in flight during pass 0
-        // ---- B. the claim
+        uint32_t nq = 0;                                               // (lane 0; claim ids stay below 2^32)
+        if (lid == 0) nq = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long *>(P.work), 1ULL);   // in flight during pass 0
+        // ---- B. the claim.  Per pass, coordinates come from the control block again (volatile shared memory: the
+        // compiler cannot keep views of the tile alive across the item and spill them)
         uint32_t bad = 0;
-        const int32_t tile = w.tile, round = w.round;
+        const int32_t passes = F.rows_per_claim;
+        for (int32_t r = 0; r < max(passes, 2); ++r) {
+            if (r < passes) {
+                const int32_t wy = 32 / (F.tl / VEC), claim_rows = wy * passes;
+                const int32_t c0 = w.chunk * claim_rows, c1 = min(c0 + claim_rows, (int32_t)P.C);
+                const int32_t lo = c0 + r * wy, hi = min(lo + wy, c1);
+                if (lo < hi) bad |= fused_claim<T, VEC, DSEL, VDEG>(F, w.tile, w.round, flags, lo, hi, lid);
+            }
+            if (r == 0) {
+                issue_count(false);                                    // the claim before this one
+                if (lid == 0) {
+                    set_coord0(nq, true);
+                    // one batch of loads for the next claim (lane 0 waits for them here; the other warps of the SM
+                    // keep the memory system busy meanwhile)
+                    const int32_t nt = w.n_tile;
+                    const int32_t p_done = ld_volatile(&P.ctrl[CTRL_COMPLETED]);
+                    const unsigned long long p_slot = *reinterpret_cast<const volatile unsigned long long *>(&F.ppq[w.ticket % (uint32_t)F.ppq_size]);
+                    const unsigned long long p_bk = ld_acquire_u64(&F.bk_word[nt]);
+                    const int32_t p_ppd = ld_volatile(&F.pp_done[nt]);
+                    w.done = p_done; w.slot = p_slot; w.bk = p_bk; w.ppd = p_ppd;
+                }
+            } else if (r == 1) {
+                if (lid == 0) w.cnt_val = cnt_r;
+                __syncwarp();
+                const bool pf = w.done < frames && (uint32_t)(w.slot >> 32) != w.ticket + 1u && tile_ready(w.n_round);
+                if (pf) n_flags = load_flags(w.n_tile);
+                __syncwarp();
+                if (lid == 0) w.n_have_flags = pf ? 1 : 0;
+                __syncwarp();
+            }
+        }
         {
-            const int32_t bx = F.tl / VEC, tx = lid % bx, tyw = lid / bx, wy = 32 / bx;
-            LaneInfo<VEC> L;
-            L.l0 = tile * F.tl + tx * VEC;
-            L.active = L.fresh = L.wpost = L.fin_ok = L.fin_fail = L.upd = 0;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                const uint32_t f = flags >> (8 * k);
-                L.active |= (f & 1u) << k;
-                L.fresh |= ((f >> 1) & 1u) << k;
-                L.wpost |= ((f >> 2) & 1u) << k;
-            }
-            const TileView<T> V = tile_view(F, round & 1, tile);
-            const uint64_t pol_ld = l2_policy(F.hints == 2 ? 2 : 0), pol_st = l2_policy(F.hints >= 1 ? 1 : 0);
-            const uint64_t pol_post = l2_policy(F.hints == 3 ? 2 : 0);   // (3: posterior columns kept for the refill)
-            const int32_t claim_rows = wy * F.rows_per_claim, C = (int32_t)P.C;
-            const int32_t c0 = w.chunk * claim_rows, c1 = min(c0 + claim_rows, C);
-            const int32_t passes = F.rows_per_claim;
-            for (int32_t r = 0; r < max(passes, 2); ++r) {
-                if (r < passes && L.active) {
-                    const int32_t lo = c0 + r * wy, hi = min(lo + wy, c1);
-                    if (lo < hi) bad |= fused_claim<T, VEC, DSEL, VDEG>(F, V, L, lo, hi, tx, tyw, wy, pol_ld, pol_st, pol_post);
-                }
-                if (r == 0) {
-                    issue_count(false);                                // the claim before this one
-                    if (lid == 0) {
-                        set_coord0(nq, true);
-                        // one batch of loads for the next claim, left in registers while pass 1 computes
-                        p_done = ld_volatile(&P.ctrl[CTRL_COMPLETED]);
-                        p_slot = *reinterpret_cast<const volatile unsigned long long *>(&F.ppq[w.ticket % (uint32_t)F.ppq_size]);
-                        p_bk = ld_acquire_u64(&F.bk_word[w.n_tile]);
-                        p_ppd = ld_volatile(&F.pp_done[w.n_tile]);
-                    }
-                } else if (r == 1) {
-                    if (lid == 0) {
-                        w.cnt_val = cnt_r;
-                        w.done = p_done; w.slot = p_slot; w.bk = p_bk; w.ppd = p_ppd;
-                    }
-                    __syncwarp();
-                    const bool pf = w.done < frames && (uint32_t)(w.slot >> 32) != w.ticket + 1u && tile_ready(w.n_round);
-                    if (pf) n_flags = load_flags(w.n_tile);
-                    __syncwarp();
-                    if (lid == 0) w.n_have_flags = pf ? 1 : 0;
-                    __syncwarp();
-                }
-            }
             // per-lane "some check unsatisfied" flags: OR over the warp's check rows, idempotent stores of 1
+            const int32_t bx = F.tl / VEC, tx = lid % bx, tyw = lid / bx, tile = w.tile;
             for (int32_t o = bx; o < 32; o <<= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
             if (tyw == 0) {
 #pragma unroll
@@ -564,7 +579,7 @@ __global__ void __launch_bounds__(kFBlock, DSEL > 0 ? 2 : 1) k_fused(const __gri
         have_flags = w.n_have_flags != 0; flags = n_flags;
         __syncwarp();
         if (lid == 0) {
-            w.sig_tile = tile; w.sig_round = round;                    // counted after pass 0 of the next claim
+            w.sig_tile = w.tile; w.sig_round = w.round;                // counted after pass 0 of the next claim
             w.round = w.n_round; w.tile = w.n_tile; w.chunk = w.n_chunk;
         }
     }

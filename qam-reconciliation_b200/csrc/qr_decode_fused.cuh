@@ -157,6 +157,32 @@ QR_HD void st_pol(V *p, const V &val, uint64_t pol)
 #endif
 }
 
+// 16-byte row accesses WITHOUT a policy register (the lean item: three 64-bit policy operands are six registers it
+// does not have): loads bypass L1 (.cg), stores are either plain or streaming (.cs: evict-first in L2, the same
+// effect as the evict_first policy of st_pol)
+QR_HD Vec<float, 4> ld_row16(const void *p)
+{
+#if defined(__CUDA_ARCH__)
+    const float4 r = __ldcg(reinterpret_cast<const float4 *>(p));
+    Vec<float, 4> v;
+    v.v[0] = r.x; v.v[1] = r.y; v.v[2] = r.z; v.v[3] = r.w;
+    return v;
+#else
+    return *reinterpret_cast<const Vec<float, 4> *>(p);
+#endif
+}
+QR_HD void st_row16(void *p, const Vec<float, 4> &val, bool streaming)
+{
+#if defined(__CUDA_ARCH__)
+    const float4 r = make_float4(val.v[0], val.v[1], val.v[2], val.v[3]);
+    if (streaming) __stcs(reinterpret_cast<float4 *>(p), r);
+    else __stcg(reinterpret_cast<float4 *>(p), r);
+#else
+    (void)streaming;
+    *reinterpret_cast<Vec<float, 4> *>(p) = val;
+#endif
+}
+
 // Posterior of the lanes in `mask` only.  A PARKED lane (finished, waiting for its sector group to be refilled) keeps
 // its posterior column until it is shipped: neighbours in the same thread's lane vector must not overwrite it.
 template <typename T, int VEC>
@@ -332,8 +358,7 @@ struct alignas(16) NbrL {
 template <int D, bool ANYFRESH>
 QR_HD uint32_t fused_item_lean(const char *llr_t, const char *cold_t, char *cnew_t, char *post_t,
                                const uint8_t *synd_t, const NbrL *rec, int32_t ci, int32_t slot0, int32_t tl,
-                               uint32_t fresh, uint32_t wpost, uint32_t active, uint64_t pol_ld, uint64_t pol_st,
-                               uint64_t pol_post)
+                               uint32_t fresh, uint32_t wpost, uint32_t active, bool stream_st)
 {
     using VT = Vec<float, 4>;
     const uint32_t rowb = (uint32_t)tl * 4u;
@@ -360,10 +385,10 @@ QR_HD uint32_t fused_item_lean(const char *llr_t, const char *cold_t, char *cnew
                 q = rec[slot0 + i];
 #endif
                 first[j] = q.first;
-                ch[j] = ld_pol(reinterpret_cast<const VT *>(llr_t + q.llr_off), pol_ld);
-                m1[j] = ld_pol(reinterpret_cast<const VT *>(cold_t + q.o1_off), pol_ld);
-                m2[j] = ld_pol(reinterpret_cast<const VT *>(cold_t + q.o2_off), pol_ld);
-                mo[j] = ld_pol(reinterpret_cast<const VT *>(own_t + (uint32_t)i * rowb), pol_ld);
+                ch[j] = ld_row16(llr_t + q.llr_off);
+                m1[j] = ld_row16(cold_t + q.o1_off);
+                m2[j] = ld_row16(cold_t + q.o2_off);
+                mo[j] = ld_row16(own_t + (uint32_t)i * rowb);
             }
         }
 #pragma unroll
@@ -387,7 +412,12 @@ QR_HD uint32_t fused_item_lean(const char *llr_t, const char *cold_t, char *cnew
 #else
                     const uint32_t off = rec[slot0 + i].llr_off;
 #endif
-                    store_post_lanes<float, 4>(reinterpret_cast<float *>(post_t + off), pv, wpost, pol_post);
+                    if (wpost == 0xfu) st_row16(post_t + off, pv, false);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (wpost >> k & 1) reinterpret_cast<float *>(post_t + off)[k] = pv.v[k];
+                    }
                 }
             }
         }
@@ -403,7 +433,7 @@ QR_HD uint32_t fused_item_lean(const char *llr_t, const char *cold_t, char *cnew
     }
     char *out_t = cnew_t + (size_t)slot0 * rowb;
 #pragma unroll
-    for (int i = 0; i < D; ++i) st_pol(reinterpret_cast<VT *>(out_t + (uint32_t)i * rowb), x[i], pol_st);
+    for (int i = 0; i < D; ++i) st_row16(out_t + (uint32_t)i * rowb, x[i], stream_st);
     return par & active;
 }
 

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqamrecon.so")
+# (QAMRECON_LIBRARY: another build of the SAME library, for A/B timing of two builds on one box -- a development aid)
+LIB_PATH = os.environ.get("QAMRECON_LIBRARY") or os.path.join(HERE, "libqamrecon.so")
 
 QR_OK, QR_ERR_INVALID, QR_ERR_GRAPH, QR_ERR_CUDA, QR_ERR_NOMEM = 0, 1, 2, 3, 4
 QR_F32, QR_F64 = 32, 64

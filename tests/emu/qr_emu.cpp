@@ -196,8 +196,8 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
                         const char *cold_t = reinterpret_cast<const char *>(V.c_old) + lt4;
                         char *cnew_t = reinterpret_cast<char *>(V.c_new) + lt4;
                         char *post_t = reinterpret_cast<char *>(V.post) + lt4;
-                        if (L.fresh) bad |= fused_item_lean<6, true>(llr_t, cold_t, cnew_t, post_t, V.synd + tx * VEC, lean.data(), ci, 6 * ci, tl, L.fresh, L.wpost, L.active, 0, 0, 0);
-                        else bad |= fused_item_lean<6, false>(llr_t, cold_t, cnew_t, post_t, V.synd + tx * VEC, lean.data(), ci, 6 * ci, tl, 0u, L.wpost, L.active, 0, 0, 0);
+                        if (L.fresh) bad |= fused_item_lean<6, true>(llr_t, cold_t, cnew_t, post_t, V.synd + tx * VEC, lean.data(), ci, 6 * ci, tl, L.fresh, L.wpost, L.active, false);
+                        else bad |= fused_item_lean<6, false>(llr_t, cold_t, cnew_t, post_t, V.synd + tx * VEC, lean.data(), ci, 6 * ci, tl, 0u, L.wpost, L.active, false);
                     }
                     for (int k = 0; k < VEC; ++k)
                         if (bad >> k & 1) P.unsat[0][L.l0 + k] = 1;

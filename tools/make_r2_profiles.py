@@ -37,7 +37,7 @@ def main():
     for rep, dst in (("r2_bench_chain_full.ncu-rep", "r2_bench_chain_ncu_full.txt"),
                      ("r2_irregular_full.ncu-rep", "r2_irregular_decoder_ncu_full.txt")):
         path = os.path.join(G, rep)
-        if not os.path.exists(path):
+        if not os.path.exists(path) and not os.path.exists(path.replace(".ncu-rep", "_raw.csv")):
             continue
         sp.kernels(path, os.path.join(P, dst))
         print("wrote", dst)
@@ -48,7 +48,11 @@ def main():
             if "k_fused" not in name:
                 continue
             g = lambda k: float(r[hdr.index(k)]) * SCALE[units[hdr.index(k)]]
-            rd, wr, l2 = g("dram__bytes_read.sum"), g("dram__bytes_write.sum"), g("lts__t_bytes.sum")
+            rd, wr = g("dram__bytes_read.sum"), g("dram__bytes_write.sum")
+            sec = lambda k: float(r[hdr.index(k)]) * 32.0          # L2 sectors are 32 bytes
+            # what the SMs moved through L2 (srcunit_tex) and what crossed between the two L2 partitions on top of it
+            l2, l2_fabric = sec("lts__t_sectors_srcunit_tex.sum"), sec("lts__t_sectors_srcunit_ltcfabric.sum")
+            l2_rd, l2_wr = sec("lts__t_sectors_srcunit_tex_op_read.sum"), sec("lts__t_sectors_srcunit_tex_op_write.sum")
             t = float(r[hdr.index("gpu__time_duration.sum")]) * TSCALE[units[hdr.index("gpu__time_duration.sum")]]
             entries.append({
                 "source": f"profiles/{dst} (ncu --set full --clock-control none -k regex:k_fused... python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-extras)",
@@ -56,7 +60,8 @@ def main():
                 "config": {"n": 64800, "frames": 4096, "max_iterations": 50, "precision": "fp32", "schedule": "fused", "lanes": 1024},
                 "frame_iterations": 4096 * 50,
                 "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
-                "l2_bytes_per_launch": l2, "l2_peak_GBps": 10000.0,
+                "l2_bytes_per_launch": l2, "l2_read_bytes": l2_rd, "l2_write_bytes": l2_wr,
+                "l2_partition_fabric_bytes": l2_fabric, "l2_peak_GBps": 10000.0,
                 "l2_peak_source": "profiles/r2_membench.txt: gathers of 128-byte rows out of a 32 MB L2-resident set, 16 warps/SM",
                 "duration_ms_under_ncu": t * 1e3})
     if entries:

@@ -30,6 +30,8 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 
 def raw(rep):
     out = rep.replace(".ncu-rep", "_raw.csv")
+    if not os.path.exists(rep):
+        return out          # exported on the GPU box already (the reports themselves are too large to bring back)
     if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(rep):
         with open(out, "w") as fh:
             subprocess.check_call(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=fh, stderr=subprocess.DEVNULL)
