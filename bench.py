@@ -119,7 +119,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         skip = getattr(self, "skip", 0)
         for s in (self.samples[skip:] or self.samples):
             f = [t.strip() for t in s.split(",")]
@@ -129,11 +129,15 @@ class ClockSampler:
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w": float(np.median(pw)) if pw else None}
 
 
 # ---------------------------------------------------------------------------------------------- CPU arms
@@ -518,9 +522,14 @@ def ours(a):
     # ---- end to end through the host-buffer C ABI
     e2e = None
     if not a.no_e2e:
+        s2 = ClockSampler(local)          # clocks of THIS leg: it and the device leg are both power-capped, differently
+        if rank == 0:
+            s2.start()
+            s2.wait_ready()
         el, h2d, d2h = wl.e2e_leg(a.steps, a.warmup, barrier)
+        e2e_clocks = s2.stop() if rank == 0 else None
         e2e = {"value": total_frames / max_over_ranks(el), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h,
+               "d2h_bytes_per_step": d2h, "clocks": e2e_clocks,
                "api": "qr_reconcile_host: host y (f64) + tx symbols (i64) in; success, iterations, bit errors and "
                       "final LLRs out; pinned host memory"}
 

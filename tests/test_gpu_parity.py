@@ -452,3 +452,28 @@ def test_reconcile_host_matches_stepwise(qr, orc):
         assert np.array_equal(post, post2.cpu().numpy())
         want = [orc.count_errors_from_lappr(post[f, :K], word[f, :K]) for f in range(frames)]
         assert list(errs) == want
+
+
+@pytest.mark.parametrize("n", [96, 100, 1297])
+def test_syndrome_of_many_frames_uses_the_staged_kernel(n):
+    """>= 256 frames take k_eval_syndrome_smem (one CTA per frame, word packed to bits in shared memory); results must
+    be those of the per-frame oracle (matrix.pyx:55-60) for frame lengths that are / are not multiples of 8 (aligned
+    and unaligned rows), and for words holding bytes other than 0 / 1 (XOR of whole bytes)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import qamreconciliation as qr
+    from qamreconciliation import codes
+    from oracle import port as orc
+    rng = np.random.default_rng(n)
+    vid, cid = codes.irregular_ldpc(n, n // 2 + 3, [2, 3, 6], [0.3, 0.5, 0.2], seed=n)
+    mat, omat = qr.Matrix(vid, cid), orc.Matrix(vid, cid)
+    frames = 300
+    w = rng.integers(0, 2, size=(frames, n)).astype(np.uint8)
+    got = mat.eval_syndrome_batch(w).cpu().numpy()
+    want = np.array([omat.eval_syndrome(r) for r in w])
+    assert np.array_equal(got, want)
+    w[7] = rng.integers(0, 256, size=n).astype(np.uint8)          # one frame of arbitrary bytes among bit frames
+    w[299, n - 1] = 2
+    got = mat.eval_syndrome_batch(w).cpu().numpy()
+    want = np.array([omat.eval_syndrome(r) for r in w])
+    assert np.array_equal(got, want)
