@@ -373,7 +373,7 @@ class Workload:
         fi, steps_exec = self.dec.last_stats(self.precision, self.lanes or None)
         return float(np.mean(kt)), fi, steps_exec
 
-    def e2e_leg(self, steps, warmup, barrier):
+    def e2e_leg(self, steps, warmup, barrier, sampler=None):
         """Through qr_reconcile_host: pinned host y / x in, success, iterations, bit errors and final LLRs out, the
         copies inside the timed region.  Returns (seconds on this rank, h2d bytes, d2h bytes per step)."""
         torch = self.torch
@@ -386,6 +386,8 @@ class Workload:
         for i in range(min(warmup, 2)):
             self.rec.run_host(hy[i % self.n_sets], hx[i % self.n_sets], self.maxiter, self.K, outs)
         barrier()
+        if sampler is not None:
+            sampler.skip = len(sampler.samples)       # (pinning the host buffers above took seconds of idle GPU)
         t0 = time.perf_counter()
         for i in range(steps):
             self.rec.run_host(hy[i % self.n_sets], hx[i % self.n_sets], self.maxiter, self.K, outs)
@@ -429,8 +431,8 @@ class Workload:
             r["dram_GBps"] = traffic / (k_ms / 1e3) / 1e9
             r["dram_frac"] = r["dram_GBps"] / peak
             if ent.get("l2_bytes_per_launch"):
-                # the level that actually bounds the fused kernel: L2 throughput (lts__t_bytes of the same capture) against
-                # the builder-measured L2 gather bandwidth (tools/membench.cu, profiles/r2_membench.txt)
+                # what the SMs moved through L2 (lts__t_sectors_srcunit_tex of the same capture, partition-fabric crossings
+                # not included) against the builder-measured L2 gather bandwidth (tools/membench.cu, profiles/r2_membench.txt)
                 r["l2_GBps"] = ent["l2_bytes_per_launch"] / (k_ms / 1e3) / 1e9
                 r["l2_peak_GBps"] = ent.get("l2_peak_GBps")
                 r["l2_frac"] = r["l2_GBps"] / ent["l2_peak_GBps"] if ent.get("l2_peak_GBps") else None
@@ -526,7 +528,7 @@ def ours(a):
         if rank == 0:
             s2.start()
             s2.wait_ready()
-        el, h2d, d2h = wl.e2e_leg(a.steps, a.warmup, barrier)
+        el, h2d, d2h = wl.e2e_leg(a.steps, a.warmup, barrier, s2)
         e2e_clocks = s2.stop() if rank == 0 else None
         e2e = {"value": total_frames / max_over_ranks(el), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "clocks": e2e_clocks,

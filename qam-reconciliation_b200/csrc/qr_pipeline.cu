@@ -228,11 +228,11 @@ static int reconcile_host_impl(qr_decoder *d, const qr_mapper *m, int mode, int 
     chunk = std::min<int64_t>(chunk, std::max<int64_t>((int64_t)d->lanes, (frames + 3) / 4));
     chunk = std::min(chunk, frames);
     // The first chunk's upload and the last chunk's download cannot hide behind kernels: make those two chunks
-    // small (a quarter of a chunk, at least 32 frames) whenever the batch is cut at all.
+    // small (a quarter of a chunk, 32 to 256 frames) whenever the batch is cut at all.
     std::vector<int64_t> cuts;    // chunk boundaries: cuts[c] .. cuts[c + 1]
     cuts.push_back(0);
     if (chunk < frames) {
-        const int64_t small = std::max<int64_t>(32, chunk / 4 / 32 * 32);
+        const int64_t small = std::max<int64_t>(32, std::min<int64_t>(256, chunk / 4 / 32 * 32));
         cuts.push_back(std::min(small, frames));
         while (frames - cuts.back() > chunk + small) cuts.push_back(cuts.back() + chunk);
         if (frames - cuts.back() > small) cuts.push_back(frames - small);
