@@ -52,7 +52,8 @@ def parse():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--demap", default="fast", choices=["fast", "exact"])
     ap.add_argument("--lanes", type=int, default=-1,
-                    help="frames resident in the decoder (0 = library default; -1 = 1024 for the fused schedule, else 0)")
+                    help="frames resident in the decoder (0 = the package's default: one lane per frame up to 4096; -1 = one lane "
+                         "per frame of the step for the fused fp32 schedule (4096), 512 for fp64, else 0)")
     ap.add_argument("--schedule", type=int, default=-1,
                     help="0 persistent two-phase kernel, 1 launch per phase, 2 fused flooding iteration (persistent); "
                          "-1 = 2")
@@ -66,7 +67,9 @@ def parse():
     if a.schedule < 0:
         a.schedule = 2
     if a.lanes < 0:
-        a.lanes = (1024 if a.precision == "fp32" else 512) if a.schedule == 2 else 0
+        # one lane per frame: no lane is ever refilled inside a step (refill generations measured ~8 % slower at 3 dB,
+        # ~15 % at 4 dB and ~20 % at 5 dB; the workspace is 1.8 MB per lane of config 2 -- 7.4 GB of the 180 GB)
+        a.lanes = ((a.frames + 31) // 32 * 32 if a.precision == "fp32" else 512) if a.schedule == 2 else 0
     return a
 
 
@@ -252,7 +255,7 @@ def workload_config(a, n_sets=2):
     B, S = a.frames, a.n // BPS
     return {"workload": workload_name(a.n, a.snr), "frames_per_gpu_per_step": B,
             "demap": a.demap + (" (fp32 grade: QR_DEMAP_FAST | QR_DEMAP_F32GRADE)" if a.demap == "fast" and a.precision == "fp32" else ""),
-            "decoder_lanes": a.lanes or 512, "schedule": {0: "persistent", 1: "launch", 2: "fused", 3: "auto"}[a.schedule],
+            "decoder_lanes": a.lanes or auto_lanes(a.frames), "schedule": {0: "persistent", 1: "launch", 2: "fused", 3: "auto"}[a.schedule],
             "l2_policy": f"{n_sets} alternating input sets of {B * S * 16 / 1e9:.1f} GB each (>> 126 MB L2)"}
 
 
@@ -440,6 +443,14 @@ class Workload:
         return r
 
 
+def auto_lanes(frames):
+    """What the package picks when no lane count is named (Decoder._auto_lanes, memory permitting)."""
+    want = 512
+    while want < min(frames, 4096):
+        want *= 2
+    return want
+
+
 def lookup_traffic(n, B, maxiter, precision, schedule, lanes, fi):
     """DRAM bytes of the same launch from the committed ncu --set full captures (profiles/r*_traffic.json)."""
     import glob
@@ -519,7 +530,7 @@ def ours(a):
     # ---- decoder kernel alone (roofline)
     k_ms, fi, steps_exec = wl.decoder_leg(max(3, a.steps))
     roofline = wl.roofline(k_ms, fi, KERNEL_NAMES[a.schedule],
-                           lookup_traffic(n, B, MAXITER, a.precision, a.schedule, a.lanes or 512, fi))
+                           lookup_traffic(n, B, MAXITER, a.precision, a.schedule, a.lanes or auto_lanes(B), fi))
 
     # ---- end to end through the host-buffer C ABI
     e2e = None
@@ -635,7 +646,7 @@ def extras(a, torch, qr, codes, dev, wl, barrier):
                "warmup": warmup, "frames_per_step": w.B, "avg_iterations": fi / w.B,
                "fer": cnt[1] / max(1, cnt[4]), "ber": cnt[0] / max(1, cnt[4] * w.K),
                "roofline": w.roofline(k_ms, fi, kname or KERNEL_NAMES[w.schedule],
-                                      lookup_traffic(w.n, w.B, w.maxiter, w.precision, w.schedule, w.lanes or 512, fi))}
+                                      lookup_traffic(w.n, w.B, w.maxiter, w.precision, w.schedule, w.lanes or auto_lanes(w.B), fi))}
         if e2e:
             el, h2d, d2h = w.e2e_leg(steps, warmup, barrier)
             rec["e2e"] = {"value": w.B * steps / el, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}

@@ -111,7 +111,10 @@ int qr_count_errors(const void *d_lappr, int dtype, const uint8_t *d_word, int64
  * Decoder._decode / decode (decoder.pyx:391-455), batched over independent frames.
  * precision QR_F64: the reference's box-plus recursion in double, same association order;
  * precision QR_F32: fast mode (exp-domain forward/backward products, float messages).
- * `lanes` = frames resident at once (rounded up to a multiple of 32; 0 = library default). */
+ * `lanes` = frames resident at once (rounded up to a multiple of 32; 0 = library default: 512, fewer if device
+ * memory is short).  A batch uses min(lanes, frames) lanes.  One lane per frame of the largest batch is the fastest
+ * setting wherever the workspace fits -- (2 E + 2 N) * sizeof(message) + C bytes per lane with the fused schedule --
+ * because no lane is then refilled mid-launch; the Python layer sizes it that way. */
 int qr_decoder_create(const qr_graph *g, int precision, int64_t lanes, qr_decoder **out);
 void qr_decoder_destroy(qr_decoder *d);
 int qr_decoder_set_schedule(qr_decoder *d, int schedule);

@@ -30,6 +30,7 @@ class Decoder:
             raise ValueError("Sizes don't match")
         self._g = _Graph(e_to_v, e_to_c)
         self._dec = {}
+        self._auto_cap = {}
 
     # -- properties (decoder.pyx:157-172) -----------------------------------------------------
     @property
@@ -63,16 +64,47 @@ class Decoder:
         self._dec = {}
 
     # -- decoder handles ------------------------------------------------------------------------
-    def _handle(self, precision, lanes=None, schedule=None):
+    def _auto_lanes(self, precision, frames):
+        """Resident frames when the caller names none: every frame of the batch its own lane, up to 4096 and a quarter
+        of the free device memory, in powers of two from 512.  More lanes than frames cost nothing (the library uses
+        min(lanes, frames)); fewer mean refill generations, which measured slower than one lane per frame at every
+        operating point of config 2."""
+        have = self._auto_cap.get(precision, 0)
+        if frames is None:
+            return have or 512
+        want = 512
+        while want < min(int(frames), 4096):
+            want *= 2
+        if want > have:
+            w = 8 if precision == _abi.QR_F64 else 4
+            per_lane = (2 * self.ednum + 2 * self.vnum) * w + self.cnum
+            try:
+                free = torch.cuda.mem_get_info()[0]
+            except Exception:
+                free = 0
+            while want > 512 and want * per_lane > free // 4:
+                want //= 2
+        return max(want, have)
+
+    def _handle(self, precision, lanes=None, schedule=None, frames=None):
+        """Decoder handle for (precision, lanes).  lanes None: QAMRECON_LANES, else sized from `frames` (see
+        _auto_lanes); that workspace only ever grows."""
         if lanes is None:
             lanes = int(os.environ.get("QAMRECON_LANES", "0"))
         if schedule is None:
             schedule = int(os.environ.get("QAMRECON_SCHEDULE", str(_abi.QR_SCHED_AUTO)))
         key = (precision, lanes)
+        create = lanes
+        if lanes == 0:
+            create = self._auto_lanes(precision, frames)
+            if key in self._dec and create > self._auto_cap.get(precision, 0):
+                _abi.lib().qr_decoder_destroy(self._dec.pop(key))
         if key not in self._dec:
             h = C.c_void_p()
-            _abi.check(_abi.lib().qr_decoder_create(self._g.h, precision, lanes, C.byref(h)))
+            _abi.check(_abi.lib().qr_decoder_create(self._g.h, precision, create, C.byref(h)))
             self._dec[key] = h
+            if lanes == 0:
+                self._auto_cap[precision] = create
         _abi.check(_abi.lib().qr_decoder_set_schedule(self._dec[key], schedule))
         return self._dec[key]
 
@@ -105,7 +137,7 @@ class Decoder:
         success = torch.empty(B, dtype=torch.uint8, device=llr.device)
         iters = torch.empty(B, dtype=torch.int32, device=llr.device)
         post = torch.empty((B, self.vnum), dtype=out_dtype, device=llr.device) if return_post else None
-        h = self._handle(prec, lanes, schedule)
+        h = self._handle(prec, lanes, schedule, frames=B)
         _abi.check(_abi.lib().qr_decode_batch(
             h, llr.data_ptr(), dtype_code(llr), sy.data_ptr(), B, max_iterations, success.data_ptr(),
             iters.data_ptr(), post.data_ptr() if post is not None else None,

@@ -47,7 +47,7 @@ class Reconciler:
             word = torch.empty((B, self.N), dtype=torch.uint8, device=dev)
             synd = torch.empty((B, self.C), dtype=torch.uint8, device=dev)
             errs = torch.empty(B, dtype=torch.int32, device=dev) if k_info is not None else None
-            h = self.dec._handle(self.prec_code, self.lanes, self.schedule)
+            h = self.dec._handle(self.prec_code, self.lanes, self.schedule, frames=B)
             _abi.check(_abi.lib().qr_reconcile_device(
                 h, self.nm._h, self.mode, self.demap_code, self.alpha, y.data_ptr(), x.data_ptr(), B,
                 int(max_iterations), int(k_info if k_info is not None else 0), ok.data_ptr(), it.data_ptr(),
@@ -100,7 +100,7 @@ class Reconciler:
         if word is not None and (word.is_cuda or tuple(word.shape) != (B, self.N) or word.dtype != torch.uint8
                                  or not word.is_contiguous()):
             raise ValueError(f"out['word'] must be a contiguous uint8 CPU tensor of shape {(B, self.N)}")
-        h = self.dec._handle(self.prec_code, self.lanes, self.schedule)
+        h = self.dec._handle(self.prec_code, self.lanes, self.schedule, frames=B)
         _abi.check(_abi.lib().qr_reconcile_host(
             h, self.nm._h, self.mode, self.demap_code, self.alpha, y.data_ptr(), x.data_ptr(), B,
             int(max_iterations), int(k_info), out["success"].data_ptr(), out["iters"].data_ptr(),
@@ -123,7 +123,7 @@ class Reconciler:
         dec = out["decisions"]
         if dec.is_cuda or dec.dtype != torch.uint8 or tuple(dec.shape) != (B, (self.N + 7) // 8) or not dec.is_contiguous():
             raise ValueError(f"out['decisions'] must be a contiguous uint8 CPU tensor of shape {(B, (self.N + 7) // 8)}")
-        h = self.dec._handle(self.prec_code, self.lanes, self.schedule)
+        h = self.dec._handle(self.prec_code, self.lanes, self.schedule, frames=B)
         _abi.check(_abi.lib().qr_reconcile_host_compact(
             h, self.nm._h, self.mode, self.demap_code, self.alpha, y32.data_ptr(), x8.data_ptr(), B,
             int(max_iterations), int(k_info), out["success"].data_ptr(), out["iters"].data_ptr(), dec.data_ptr(),

@@ -104,3 +104,28 @@ def test_fused_equals_two_phase(seed, monkeypatch):
         ok, it, post = odec.decode(llr[f], synd[f], maxiter)
         assert (int(a[0][f]), int(a[1][f])) == (ok, it)
         np.testing.assert_allclose(a[2][f].cpu().numpy(), post, rtol=1e-9, atol=1e-9)
+
+
+def test_default_lane_count_follows_the_batch(monkeypatch):
+    """lanes=None: one lane per frame (powers of two from 512 up to 4096, the workspace only grows); the results are
+    those of any explicit lane count, bit for bit in fp64 -- with refills (64 lanes) and without (default)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import qamreconciliation as qr
+    from qamreconciliation import codes, _abi
+    from oracle import port as orc
+    monkeypatch.delenv("QAMRECON_LANES", raising=False)
+    rng = np.random.default_rng(77)
+    vid, cid = codes.regular_ldpc(240, 3, 6, seed=5)
+    dec = qr.Decoder(vid, cid)
+    for frames, cap in ((40, 512), (1300, 2048), (700, 2048)):
+        llr, synd = frames_for(orc, vid, cid, frames, rng)
+        a = dec.decode_batch(llr, synd, 12, precision="fp64", schedule=2)
+        assert dec._auto_cap[_abi.QR_F64] == cap
+        b = dec.decode_batch(llr, synd, 12, precision="fp64", schedule=2, lanes=64)
+        c = dec.decode_batch(llr, synd, 12, precision="fp64", schedule=0)
+        for x in (b, c):
+            assert torch.equal(a[0], x[0]) and torch.equal(a[1], x[1])
+            assert torch.equal(a[2].view(torch.int64), x[2].view(torch.int64))
+        fi, _ = dec.last_stats("fp64")
+        assert fi == int(torch.where(a[0].bool(), a[1], torch.full_like(a[1], 12)).sum())

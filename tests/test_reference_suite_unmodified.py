@@ -61,7 +61,7 @@ def test_reference_test_decoder_runs_unmodified():
     assert lines[0].startswith(PKG) and lines[1].startswith(STUBS), probe.stdout + probe.stderr
 
 
-@pytest.mark.parametrize("flags,snr", [([], ("3.0", "6.0")), (["--hard"], ("5.0", "8.0")), (["--direct"], ("3.0", "6.0"))])
+@pytest.mark.parametrize("flags,snr", [([], ("3.0", "6.0")), (["--hard"], ("4.0", "8.0")), (["--direct"], ("3.0", "6.0"))])
 def test_reference_sim_script_runs_unmodified(tmp_path, flags, snr):
     """`python sims/sim_reconciliation.py EDGEFILE ...` of the reference, by path, unchanged: BER/FER fall from 1
     below the waterfall to 0 above it."""

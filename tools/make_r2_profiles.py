@@ -24,6 +24,14 @@ def copy(src, dst):
 
 
 def main():
+    global LANES
+    try:
+        # (the ncu captures run bench.py with its defaults: the lane count of the newest default-run record)
+        newest = max((f for f in ("r2_bench_n1_3dB.json", "r2_bench_quick.json") if os.path.exists(os.path.join(G, f))),
+                     key=lambda f: os.path.getmtime(os.path.join(G, f)))
+        LANES = json.loads(open(os.path.join(G, newest)).read().strip().splitlines()[-1])["config"]["decoder_lanes"]
+    except Exception:
+        LANES = 4096
     copy("r2_bench_n1_3dB.json", "r2_bench_n1_3dB.json")
     copy("r2_bench_reference_arm.json", "r2_bench_reference_arm.json")
     copy("r2_membench.txt", "r2_membench.txt")
@@ -57,7 +65,7 @@ def main():
             entries.append({
                 "source": f"profiles/{dst} (ncu --set full --clock-control none -k regex:k_fused... python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-extras)",
                 "kernel": name.split("(")[0].replace("void qr::", ""),
-                "config": {"n": 64800, "frames": 4096, "max_iterations": 50, "precision": "fp32", "schedule": "fused", "lanes": 1024},
+                "config": {"n": 64800, "frames": 4096, "max_iterations": 50, "precision": "fp32", "schedule": "fused", "lanes": LANES},
                 "frame_iterations": 4096 * 50,
                 "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
                 "l2_bytes_per_launch": l2, "l2_read_bytes": l2_rd, "l2_write_bytes": l2_wr,
