@@ -340,8 +340,11 @@ class Workload:
         b_frames = torch.tensor(self.B, dtype=torch.int64, device=self.dev)
         barrier()
         ev[0].record()
+        marks = []
         for i in range(steps):
             out = self.step(warmup + i)
+            if os.environ.get("QAMRECON_BENCH_STEP_TIMES"):            # diagnostic: per-step device times on stderr
+                marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record()
             # (b_frames lives on the device: building it here would be a synchronous host-to-device copy every
             # step, which stalls the launch queue behind the whole step)
             counters += torch.stack([out["bit_errors"].sum(dtype=torch.int64), (out["bit_errors"] > 0).sum(),
@@ -352,6 +355,10 @@ class Workload:
             all_reduce(counters)                      # BER / FER / iteration counters: one tiny NCCL all-reduce
         ev[1].record()
         barrier()
+        if marks:
+            torch.cuda.synchronize()
+            t = [ev[0].elapsed_time(m) for m in marks]
+            sys.stderr.write("step end times [ms]: " + " ".join(f"{x:.1f}" for x in t) + "\n")
         return ev[0].elapsed_time(ev[1]), counters
 
     def decoder_leg(self, reps):

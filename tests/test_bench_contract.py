@@ -75,7 +75,7 @@ def test_round2_records_carry_the_wider_contract():
     for n in (2, 4, 8):
         r = json.loads(open(os.path.join(ROOT, "profiles", f"r2_bench_n{n}.json")).read().strip().splitlines()[-1])
         assert r["n_gpus"] == n and r["scaling"] == "weak" and r["gpu_launches"] == 7 * r["steps"] * n
-        assert r["value"] > 0.8 * n * rec["value"] or n == 4          # (the 4-GPU run had one slow rank: profiles/README.md)
+        assert r["value"] > 0.9 * n * rec["value"]
     tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
     ent = tj["entries"][-1]
     assert ent["config"] == {"n": 64800, "frames": 4096, "max_iterations": 50, "precision": "fp32", "schedule": "fused",
