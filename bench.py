@@ -330,27 +330,42 @@ class Workload:
         """W untimed + K timed steps with the inputs resident in HBM; the counters (and, on N > 1, their all-reduce:
         the path's only exchange) are inside the timed region.  Returns (elapsed ms on this rank, counters)."""
         torch = self.torch
+        # (b_frames lives on the device: building it per step would be a synchronous host-to-device copy every step,
+        # which stalls the launch queue behind the whole step)
+        b_frames = torch.tensor(self.B, dtype=torch.int64, device=self.dev)
+
+        def tally(counters, out):
+            counters += torch.stack([out["bit_errors"].sum(dtype=torch.int64), (out["bit_errors"] > 0).sum(),
+                                     out["success"].sum(dtype=torch.int64),
+                                     (out["iters"].to(torch.int64) * out["success"].to(torch.int64)).sum(),
+                                     b_frames])
+
+        # The warm-up steps do EVERYTHING a timed step does, in the same way.  Two things used to fall into the timed
+        # region otherwise, both between its first and second step (per-step event marks, QAMRECON_BENCH_STEP_TIMES):
+        # the first need for a SECOND set of output buffers (the previous step's outputs are still referenced while
+        # the next step allocates: a cudaMalloc of ~1.4 GB, ~100 ms), and the first use of torch's reduction kernels
+        # in the tally (lazy module loading waits for the device: 25-45 ms).
+        out, scratch = None, torch.zeros(5, dtype=torch.int64, device=self.dev)
         for i in range(warmup):
-            self.step(i)
+            out = self.step(i)
+            tally(scratch, out)
+        if all_reduce is not None:
+            all_reduce(scratch)
         barrier()
         if sampler is not None:
             sampler.skip = len(sampler.samples)       # samples taken before the timed region do not count
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         counters = torch.zeros(5, dtype=torch.int64, device=self.dev)
-        b_frames = torch.tensor(self.B, dtype=torch.int64, device=self.dev)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)] if os.environ.get("QAMRECON_BENCH_STEP_TIMES") else []
+        for m in marks:
+            m.record()                                # (created here, outside the timed region)
         barrier()
         ev[0].record()
-        marks = []
         for i in range(steps):
             out = self.step(warmup + i)
-            if os.environ.get("QAMRECON_BENCH_STEP_TIMES"):            # diagnostic: per-step device times on stderr
-                marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record()
-            # (b_frames lives on the device: building it here would be a synchronous host-to-device copy every
-            # step, which stalls the launch queue behind the whole step)
-            counters += torch.stack([out["bit_errors"].sum(dtype=torch.int64), (out["bit_errors"] > 0).sum(),
-                                     out["success"].sum(dtype=torch.int64),
-                                     (out["iters"].to(torch.int64) * out["success"].to(torch.int64)).sum(),
-                                     b_frames])
+            if marks:                                 # diagnostic: per-step device times on stderr
+                marks[i].record()
+            tally(counters, out)
         if all_reduce is not None:
             all_reduce(counters)                      # BER / FER / iteration counters: one tiny NCCL all-reduce
         ev[1].record()
