@@ -255,6 +255,14 @@ int qr_reconcile_host_compact(qr_decoder *d, const qr_mapper *m, int mode, int d
                               int64_t k_info, uint8_t *h_success, int32_t *h_iters, uint8_t *h_decisions_packed,
                               int32_t *h_bit_errors, void *stream);
 
+/* The chunk boundaries qr_reconcile_host (compact = 0) / qr_reconcile_host_compact (compact = 1) use for a batch of
+ * `frames` frames on a decoder with `lanes` resident frames (host logic only, no device work): cuts[0] = 0 < cuts[1] < ... < cuts[n_cuts - 1] = frames.
+ * Chunks flow through upload / kernels / download on three streams; a chunk never exceeds the lanes when a quarter
+ * of the batch fits them (no lane is refilled), and the batch ramps up and down (reference types: 64, 192, 576, ...,
+ * 320, 64 frames; compact: one piece of at most 256 frames at either end) so that only those copies are exposed.  (The reference has no counterpart: sims/reconciliation.pyx:127-161
+ * handles one frame at a time in host memory.) */
+int qr_host_chunk_cuts(int64_t frames, int64_t lanes, int compact, int64_t *cuts, int32_t max_cuts, int32_t *n_cuts);
+
 #ifdef __cplusplus
 }
 #endif

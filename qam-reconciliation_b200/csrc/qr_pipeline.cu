@@ -166,6 +166,65 @@ extern "C" int qr_reconcile_device(qr_decoder *d, const qr_mapper *m, int mode, 
                      synd, llr, llr_dtype, d_success, d_iters, post, post_dtype, d_bit_errors, st);
 }
 
+// How qr_reconcile_host cuts a batch into chunks that flow through upload / kernels / download.
+//  * Size: about eight chunks per batch and two decoder fills per chunk (with fewer lanes than frames, continuous
+//    batching needs more frames than lanes to keep the lanes busy), never fewer than four chunks when the batch
+//    allows it; and when a quarter of the batch fits the resident lanes, exactly that: four chunks hide the copies
+//    and a chunk that fits its lanes never refills one (refill generations cost ~8 % at 3 dB).
+//  * Ends: the first chunk's upload and the last chunk's download cannot hide behind kernels, so the batch ramps
+//    up and down.  On B200 an upload in the reference's types runs ~3x as fast as the kernels consume frames and a
+//    download ~6x: each head piece is 3x the one before it (its upload hides behind the kernels of the previous
+//    piece), the tail pieces shrink 5x (64, 192, 576, full ..., 320, 64 for quarters of 1024 frames).  Batches
+//    too small for the ramp, and the compact wire format (a third of the upload, next to no download: the ramp's
+//    extra launches cost more than they hide), get one small piece at either end (a quarter of a chunk, 32 to 256
+//    frames).
+static std::vector<int64_t> host_chunk_cuts(int64_t frames, int64_t lanes, bool compact)
+{
+    std::vector<int64_t> cuts;
+    cuts.push_back(0);
+    if (frames <= 0) return cuts;
+    int64_t chunk = std::max<int64_t>(2 * lanes, (frames + 7) / 8);
+    chunk = std::min<int64_t>(chunk, std::max<int64_t>(lanes, (frames + 3) / 4));
+    const int64_t quarter = ((frames + 3) / 4 + 31) / 32 * 32;
+    const int64_t piece = std::max<int64_t>(quarter, 256);     // (below 8 lane tiles a launch is latency-bound: do not cut finer)
+    if (lanes >= piece) chunk = piece;
+    chunk = std::min(chunk, frames);
+    if (chunk < frames) {
+        std::vector<int64_t> up, down;
+        for (int64_t x = 64; x < chunk; x *= 3) up.push_back(x);
+        for (int64_t x = 64; x < chunk && down.size() < 2; x *= 5) down.push_back(x);
+        int64_t ramp = 0;
+        for (int64_t x : up) ramp += x;
+        for (int64_t x : down) ramp += x;
+        if (!compact && !up.empty() && frames >= ramp + chunk) {
+            int64_t tail = 0;
+            for (int64_t x : down) tail += x;
+            for (int64_t x : up) cuts.push_back(cuts.back() + x);
+            while (frames - tail - cuts.back() > chunk) cuts.push_back(cuts.back() + chunk);
+            if (frames - tail > cuts.back()) cuts.push_back(frames - tail);
+            for (size_t i = down.size(); i-- > 0;) cuts.push_back(cuts.back() + down[i]);
+        } else {
+            const int64_t small = std::max<int64_t>(32, std::min<int64_t>(256, chunk / 4 / 32 * 32));
+            cuts.push_back(std::min(small, frames));
+            while (frames - cuts.back() > chunk + small) cuts.push_back(cuts.back() + chunk);
+            if (frames - cuts.back() > small) cuts.push_back(frames - small);
+        }
+    }
+    if (cuts.back() < frames) cuts.push_back(frames);
+    return cuts;
+}
+
+extern "C" int qr_host_chunk_cuts(int64_t frames, int64_t lanes, int compact, int64_t *cuts, int32_t max_cuts,
+                                  int32_t *n_cuts)
+{
+    if (frames < 0 || lanes <= 0 || !cuts || !n_cuts || max_cuts < 2) return qr::fail(QR_ERR_INVALID, "bad arguments");
+    const std::vector<int64_t> c = host_chunk_cuts(frames, lanes, compact != 0);
+    if ((int64_t)c.size() > max_cuts) return qr::fail(QR_ERR_INVALID, "cut array too small");
+    for (size_t i = 0; i < c.size(); ++i) cuts[i] = c[i];
+    *n_cuts = (int32_t)c.size();
+    return QR_OK;
+}
+
 static int reconcile_host_impl(qr_decoder *d, const qr_mapper *m, int mode, int demap_mode, double alpha,
                                const double *h_y, const int64_t *h_tx_index, const float *h_y32, const uint8_t *h_tx8,
                                int64_t frames, int32_t max_iterations, int64_t k_info, uint8_t *h_success,
@@ -221,27 +280,9 @@ static int reconcile_host_impl(qr_decoder *d, const qr_mapper *m, int mode, int 
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     qr::DeviceGuard guard(d->device);
 
-    // chunking: about eight chunks per batch and two decoder fills per chunk (continuous batching needs more
-    // frames than lanes to keep the lanes busy), but never fewer than four chunks when the batch allows it --
-    // with fewer, the first chunk's upload and the last chunk's download are no longer hidden
-    int64_t chunk = std::max<int64_t>(2 * (int64_t)d->lanes, (frames + 7) / 8);
-    chunk = std::min<int64_t>(chunk, std::max<int64_t>((int64_t)d->lanes, (frames + 3) / 4));
-    // ... and when a quarter of the batch fits the resident lanes, exactly that: four chunks hide the copies, and a
-    // chunk that fits its lanes never refills one (measured: refill generations cost ~8 % at 3 dB)
-    const int64_t quarter = ((frames + 3) / 4 + 31) / 32 * 32;
-    if ((int64_t)d->lanes >= quarter) chunk = quarter;
-    chunk = std::min(chunk, frames);
-    // The first chunk's upload and the last chunk's download cannot hide behind kernels: make those two chunks
-    // small (a quarter of a chunk, 32 to 256 frames) whenever the batch is cut at all.
-    std::vector<int64_t> cuts;    // chunk boundaries: cuts[c] .. cuts[c + 1]
-    cuts.push_back(0);
-    if (chunk < frames) {
-        const int64_t small = std::max<int64_t>(32, std::min<int64_t>(256, chunk / 4 / 32 * 32));
-        cuts.push_back(std::min(small, frames));
-        while (frames - cuts.back() > chunk + small) cuts.push_back(cuts.back() + chunk);
-        if (frames - cuts.back() > small) cuts.push_back(frames - small);
-    }
-    if (cuts.back() < frames) cuts.push_back(frames);
+    const std::vector<int64_t> cuts = host_chunk_cuts(frames, d->lanes, compact);    // chunk boundaries: cuts[c] .. cuts[c + 1]
+    int64_t chunk = 0;                                                        // largest piece: what the buffers hold
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) chunk = std::max(chunk, cuts[c + 1] - cuts[c]);
     const int64_t n_chunks = (int64_t)cuts.size() - 1;
     const int n_sets = n_chunks > 1 ? 2 : 1;
 

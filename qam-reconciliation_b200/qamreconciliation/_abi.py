@@ -68,6 +68,7 @@ SIGNATURES = {
                                             _vp, _vp]),
     "qr_reconcile_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f64, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp,
                                     C.c_int, _vp, _vp, _vp]),
+    "qr_host_chunk_cuts": (C.c_int, [_i64, _i64, C.c_int, _P(_i64), _i32, _P(_i32)]),
 }
 
 _lib = None

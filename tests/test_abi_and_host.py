@@ -148,3 +148,37 @@ def test_code_generator_and_csv_roundtrip(tmp_path):
     assert np.array_equal(rv, vid) and np.array_equal(rc, cid)
     hv, hc = codes.hamming_7_4()
     assert hv.size == 12 and hc.max() == 2 and hv.max() == 6
+
+
+def test_host_pipeline_chunk_cuts():
+    """qr_host_chunk_cuts (host logic of qr_reconcile_host, no device): the cuts cover the batch, no chunk exceeds the
+    resident lanes when a quarter of the batch fits them (so no lane is ever refilled), the head ramps up by at most
+    3x per piece from 64 frames and the tail ends on 64 -- only those two copies are exposed."""
+    import sys
+    sys.path.insert(0, PKG)
+    from qamreconciliation import _abi
+    L = _abi.lib()
+
+    def cuts(frames, lanes, compact=0):
+        buf = (C.c_int64 * 256)(); n = C.c_int32()
+        assert L.qr_host_chunk_cuts(frames, lanes, compact, buf, 256, C.byref(n)) == 0
+        return list(buf[:n.value])
+
+    assert cuts(4096, 4096) == [0, 64, 256, 832, 1856, 2880, 3712, 4032, 4096]
+    assert cuts(4096, 1024) == cuts(4096, 4096)                  # quarters of 1024 frames either way
+    assert cuts(4096, 4096, compact=1) == [0, 256, 1280, 2304, 3328, 3840, 4096]
+    assert cuts(100, 512) == [0, 100] and cuts(0, 512) == [0]
+    for frames in (1, 31, 64, 500, 1000, 2048, 4095, 4096, 10000, 65536):
+        for lanes in (32, 128, 512, 1024, 4096):
+            c = cuts(frames, lanes)
+            assert c[0] == 0 and c[-1] == frames and all(b > a for a, b in zip(c, c[1:])), (frames, lanes, c)
+            sizes = [b - a for a, b in zip(c, c[1:])]
+            quarter = max(256, ((frames + 3) // 4 + 31) // 32 * 32)
+            if lanes >= quarter:
+                assert max(sizes) <= lanes
+            if len(sizes) >= 6 and max(sizes) >= 256:             # ramped
+                assert sizes[0] == 64 and sizes[-1] == 64
+                assert all(b <= 3 * a for a, b in zip(sizes[:3], sizes[1:4]))
+    buf = (C.c_int64 * 2)(); n = C.c_int32()
+    assert L.qr_host_chunk_cuts(4096, 1024, 0, buf, 2, C.byref(n)) != 0     # cut array too small
+    assert L.qr_host_chunk_cuts(-1, 1024, 0, buf, 2, C.byref(n)) != 0
