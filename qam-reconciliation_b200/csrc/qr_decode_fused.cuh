@@ -95,7 +95,6 @@ struct FusedParams {
     int32_t rows_per_claim;   // checks per thread and claim
     int32_t park_rounds; // a finished lane waits up to this many rounds for the other lanes of its 8-lane sector group, so
                          // that the group is shipped and refilled together (one sector per row for 8 frames); 0: never
-    int32_t dbg;         // timing experiments (QAMRECON_FUSED_DBG): 1 no release fence (INCORRECT), 2 plain load of the tile word
     // tile pipeline (device arrays, [tiles] each; monotonic counters)
     int32_t pp_items;    // R: items per PP
     int32_t *f_done;     // finished claims of the tile, all rounds

@@ -152,7 +152,7 @@ static int emu_decode_fused_t(const qr_graph &g, int lanes, int tl, const void *
     F.nbr_lean = nullptr;
     F.c2v[0] = c2v0.data(); F.c2v[1] = c2v1.data();
     const int tiles = lanes / tl;
-    F.tl = tl; F.tiles = tiles; F.hints = 0; F.rows_per_claim = 2; F.pp_items = 3; F.dbg = 0; F.park_rounds = park_rounds;
+    F.tl = tl; F.tiles = tiles; F.hints = 0; F.rows_per_claim = 2; F.pp_items = 3; F.park_rounds = park_rounds;
     std::vector<T> postw((size_t)g.N * lanes, (T)-7e29);
     F.post = store_post ? postw.data() : nullptr;
     std::vector<int32_t> tile_minfin(tiles, 0x7fffffff), rcount(tiles, 0);
