@@ -83,6 +83,7 @@ def test_reference_sim_script_runs_unmodified(tmp_path, flags, snr):
     df = pd.read_csv(out)
     assert list(df.columns[1:]) == ["EsN0dB", "ber", "fer", "iters"] and len(df) == 3
     assert np.allclose(df.EsN0dB, np.linspace(float(snr[0]), float(snr[1]), 3))
-    assert df.fer.iloc[0] > 0.5 and df.fer.iloc[-1] == 0.0 and df.ber.iloc[-1] == 0.0
+    # (the script seeds nothing, like the reference: thresholds leave room for the Monte-Carlo spread of 300 frames)
+    assert df.fer.iloc[0] > 0.5 and df.fer.iloc[-1] <= 0.01 and df.ber.iloc[-1] <= 1e-4
     assert df.ber.iloc[0] > df.ber.iloc[1] >= df.ber.iloc[2]
     assert 0 < df.iters.iloc[-1] < 15
