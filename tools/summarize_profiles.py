@@ -54,6 +54,19 @@ def kernels(rep, dst):
             t = float(r[hdr.index('gpu__time_duration.sum')])
             tu = {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1}[units[hdr.index('gpu__time_duration.sum')]]
             fh.write(f"{'derived: DRAM traffic (read+write) / duration':82s} {(rd + wr) * scale / (t * tu) / 1e9:22.1f} GB/s\n")
+            def sectors(k):
+                try:
+                    return float(r[hdr.index(k)]) * 32.0 if k in hdr else None
+                except ValueError:
+                    return None
+            tex, fab = sectors("lts__t_sectors_srcunit_tex.sum"), sectors("lts__t_sectors_srcunit_ltcfabric.sum")
+            if tex is not None:
+                # (lts__t_bytes is not in the --set full export of this ncu; sectors are 32 bytes.  srcunit_tex = what the SMs
+                # moved through L2; ltcfabric = the same requests crossing between the two L2 partitions, on top)
+                fh.write(f"{'derived: SM<->L2 traffic (lts__t_sectors_srcunit_tex x 32 B)':82s} {tex / 1e9:22.3f} GB\n")
+                fh.write(f"{'derived: SM<->L2 traffic / duration':82s} {tex / (t * tu) / 1e9:22.1f} GB/s\n")
+            if fab is not None:
+                fh.write(f"{'derived: L2 partition fabric traffic (lts__t_sectors_srcunit_ltcfabric x 32 B) / duration':82s} {fab / (t * tu) / 1e9:22.1f} GB/s\n")
             if "lts__t_bytes.sum" in hdr:
                 lb = float(r[hdr.index("lts__t_bytes.sum")]) * {"Tbyte": 1e12, "Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[units[hdr.index("lts__t_bytes.sum")]]
                 fh.write(f"{'derived: L2 traffic (lts__t_bytes) / duration':82s} {lb / (t * tu) / 1e9:22.1f} GB/s\n")
